@@ -1,0 +1,211 @@
+/*
+ * pcr.h — C ABI of the B200-native point-cloud sphere renderer ("pcr").
+ *
+ * This is the drop-in boundary for the one hot path of EvaShenLu/PointCloud_Render:
+ * everything the reference does between "a frame's (N,3|6) point array" and
+ * "an image", i.e. its L2 scene emission + L1 Mitsuba render:
+ *
+ *   standardize_point_cloud     example_renderer.py:94-98, traj_ball_renderer.py:190-202
+ *   axis transform              example_renderer.py:171-173, traj_ball_renderer.py:204-221,
+ *                               traj_b0.py:62-82 (no x flip)
+ *   compute_color hook          example_renderer.py:89-92,115-124
+ *   generate_xml_content        example_renderer.py:113-128   (eliminated: data stays in HBM)
+ *   render_scene                example_renderer.py:153-157   (mi.load_file + mi.render)
+ *   save_scene (sRGB8 part)     example_renderer.py:159-161   (linear -> sRGB -> u8; PNG stays on host)
+ *
+ * The reference has no FFI of its own; its seam is the render_scene/save_scene
+ * pair.  INTEGRATION.md shows the ctypes stub a maintainer adds.
+ *
+ * Conventions
+ *   - plain C types only; every d_* pointer is CALLER-OWNED DEVICE memory, every
+ *     h_* pointer is host memory; the context owns only scratch.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *     All work is stream-ordered and asynchronous; no entry point synchronises
+ *     the device unless its comment says so.
+ *   - return 0 on success, negative pcr_status otherwise; the message is kept
+ *     per context (pcr_last_error). No C++ exception crosses this boundary.
+ *   - one context per (GPU, host thread); a context is not thread-safe.
+ *   - there is NO CPU fallback: without a CUDA device pcr_create fails.
+ */
+#ifndef PCR_H_
+#define PCR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCR_ABI_VERSION 1
+
+/* Point ids stored in the low 32 bits of a visibility key. */
+#define PCR_ID_FLOOR 0xFFFFFFFEu
+#define PCR_ID_MISS  0xFFFFFFFFu
+/* key = (float_as_uint(depth) << 32) | id ; depth = camera-space z of the hit (> 0).
+ * A pixel that nothing covers holds depth = +inf, id = PCR_ID_MISS.              */
+#define PCR_KEY_MISS 0x7F800000FFFFFFFFull
+
+typedef enum pcr_status {
+    PCR_OK = 0,
+    PCR_ERR_INVALID = -1,   /* bad argument                                   */
+    PCR_ERR_CUDA = -2,      /* a CUDA runtime call failed                     */
+    PCR_ERR_CAPACITY = -3,  /* n / W / H / batch larger than the context      */
+    PCR_ERR_NCCL = -4,      /* NCCL missing or a collective failed            */
+    PCR_ERR_NOMEM = -5
+} pcr_status;
+
+/* Colour hook modes (compute_color, example_renderer.py:89-92).  Mode 0 is the
+ * reference's behaviour; 1-3 are the extensions BASELINE.json's north_star names. */
+enum {
+    PCR_COLOR_CONST = 0,     /* constant const_rgb (reference: 0.3 grey)                  */
+    PCR_COLOR_POSITION = 1,  /* colormap of (p-min)/(range+1e-8), example_renderer.py:121 */
+    PCR_COLOR_VELOCITY = 2,  /* ramp on min(|v|/vel_norm,1), traj_ball_renderer.py:134    */
+    PCR_COLOR_USER = 3       /* caller-supplied per-point RGB                             */
+};
+
+/* <sensor type="perspective"> block of XMLTemplates.HEAD (example_renderer.py:16-31). */
+typedef struct pcr_camera {
+    float origin[3];
+    float target[3];
+    float up[3];
+    float fov_x_deg;   /* horizontal field of view, degrees */
+    float near_clip;
+    float far_clip;
+    int32_t width;
+    int32_t height;
+} pcr_camera;
+
+/* Scene constants of XMLTemplates.BALL_SEGMENT / TAIL (example_renderer.py:41-72)
+ * plus the axis-transform flavour (traj_ball_renderer.py:204-221 vs traj_b0.py:62-82). */
+typedef struct pcr_style {
+    int32_t color_mode;
+    float const_rgb[3];
+    float radius;        /* sphere radius when no per-point radius is given (0.01) */
+    int32_t flip_x;      /* 1: pos' = (-z, x, y+z_lift); 0: (z, x, y+z_lift)       */
+    float z_lift;        /* 0.0125                                                */
+    float vel_norm;      /* 10.0                                                  */
+    int32_t has_floor;
+    float floor_z;
+    float floor_min[2];  /* world x,y extent of the ground rectangle              */
+    float floor_max[2];
+    float floor_albedo;  /* diffuse reflectance of the ground (1.0)               */
+    float light_z;       /* area emitter: square |x|,|y| <= light_half at z       */
+    float light_half;
+    float radiance;
+    float bounce;        /* weight of the ground-bounce term on spheres (1.0)     */
+    float reserved;
+} pcr_style;
+
+/* f32 camera frame derived on the HOST in double precision from a pcr_camera.
+ * Kernels and the parity oracle consume exactly these numbers. */
+typedef struct pcr_frame {
+    float L[3];          /* camera x axis ("left")  = normalize(up x dir)   */
+    float U[3];          /* camera y axis ("newup") = dir x left            */
+    float D[3];          /* viewing direction       = normalize(target-origin) */
+    float O[3];          /* eye                                              */
+    float T;             /* tan(fov_x/2)                                     */
+    float Th;            /* T * H / W                                        */
+    float TW;            /* T / W                                            */
+    float near_clip;
+    float far_clip;
+    int32_t W;
+    int32_t H;
+} pcr_frame;
+
+typedef struct pcr_ctx pcr_ctx;
+
+int pcr_abi_version(void);
+
+/* Allocates scratch for up to max_points points per frame, max_w x max_h pixels and
+ * max_batch frames in flight per launch.  pair_capacity = max (tile, sphere) pairs per
+ * frame (0 = default 8*max_points + 65536); frames that exceed it take the slower
+ * un-binned raster, results are identical.  Synchronous. */
+int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max_h,
+               int max_batch, int64_t pair_capacity);
+void pcr_destroy(pcr_ctx* ctx);
+const char* pcr_last_error(const pcr_ctx* ctx);
+
+/* Host helper: the derived camera frame (no GPU work). */
+int pcr_camera_frame(const pcr_camera* cam, pcr_frame* out);
+
+/* K0+K1 — standardize_point_cloud + axis transform + colour hook for ONE frame.
+ *   d_in       (n, cols) row-major, float32 or float64 (in_is_f64), cols = 3 or 6
+ *   d_radius   optional per-point radius [n] (NULL -> style->radius)
+ *   d_rgb      optional per-point RGB [n][3] for PCR_COLOR_USER
+ *   d_pos_out  [n] float4 = (x', y', z', radius)      transformed positions
+ *   d_attr_out [n] float4 = (r, g, b, |v|)            colour hook output
+ *   d_vel_out  optional [n] float4 = (vx', vy', vz', 0)  transformed velocities (cols==6)
+ *   d_stats    optional device double[10]: mean xyz, min xyz, max xyz, scale (input axes)
+ */
+int pcr_standardize(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols,
+                    const float* d_radius, const float* d_rgb, const pcr_style* style,
+                    float* d_pos_out, float* d_attr_out, float* d_vel_out, double* d_stats,
+                    void* stream);
+
+/* K2+K3(+K4) — render already-transformed spheres (what generate_xml_content would emit).
+ *   d_pos    [n] float4 (x,y,z,r) world space ; d_attr [n] float4 (r,g,b,_)
+ *   id_base  added to the local index to form the stored point id (point sharding)
+ *   d_vis    [H][W] uint64 keys, written in full (required)
+ *   d_rgba   [H][W][4] uint8 sRGB image, or NULL to skip shading
+ */
+int pcr_render(pcr_ctx* ctx, const float* d_pos, const float* d_attr, int64_t n,
+               uint32_t id_base, const pcr_camera* cam, const pcr_style* style,
+               uint64_t* d_vis, uint8_t* d_rgba, void* stream);
+
+/* K4 alone — shade a (possibly merged) visibility buffer.  Points whose id is outside
+ * [id_base, id_base+n) are shaded only when owner_only == 0 is impossible for them, so:
+ *   owner_only = 0: every sphere id must be local (single GPU);
+ *   owner_only = 1: pixels won by a non-local sphere are written as 0,0,0,0 and floor /
+ *                   miss pixels are written only when id_base == 0 (rank 0), so that a
+ *                   byte-wise MAX all-reduce of the images assembles the frame. */
+int pcr_shade(pcr_ctx* ctx, const uint64_t* d_vis, const float* d_pos, const float* d_attr,
+              int64_t n, uint32_t id_base, int owner_only, const pcr_camera* cam,
+              const pcr_style* style, uint8_t* d_rgba, void* stream);
+
+/* Whole hot path for a trajectory: n_frames frames of (n, cols) points, resident on the
+ * device, -> visibility keys and sRGB8 images.  Frames are batched max_batch per launch.
+ *   d_in   [n_frames][n][cols] ; cams: HOST array of n_frames cameras
+ *   d_vis  [n_frames][H][W] or NULL ; d_rgba [n_frames][H][W][4] (required)
+ */
+int pcr_render_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols,
+                      int n_frames, const float* d_radius, const float* d_rgb,
+                      const pcr_camera* cams, const pcr_style* style,
+                      uint64_t* d_vis, uint8_t* d_rgba, void* stream);
+
+/* Same with HOST buffers: h_in is copied host->device and h_rgba (and h_vis if not NULL)
+ * device->host in chunks on two internal streams so copies overlap the kernels.
+ * Pinned host memory makes the copies asynchronous.  Synchronous: returns when the
+ * images are in h_rgba. */
+int pcr_render_frames_host(pcr_ctx* ctx, const void* h_in, int in_is_f64, int64_t n, int cols,
+                           int n_frames, const float* h_radius, const float* h_rgb,
+                           const pcr_camera* cams, const pcr_style* style,
+                           uint64_t* h_vis, uint8_t* h_rgba);
+
+/* d_dst[i] = min(d_dst[i], d_src[i]) on uint64 keys — the local half of a z-buffer merge. */
+int pcr_zmin(pcr_ctx* ctx, uint64_t* d_dst, const uint64_t* d_src, int64_t n_px, void* stream);
+
+/* C1 — in-place ncclAllReduce(d_vis, n_px, ncclUint64, ncclMin) over NVLink.
+ * `comm` is an ncclComm_t; NCCL is resolved from the running process (dlsym), so the
+ * library has no link-time NCCL dependency. */
+int pcr_zmerge_nccl(pcr_ctx* ctx, uint64_t* d_vis, int64_t n_px, void* comm, void* stream);
+
+/* Point-sharded standardisation, step 1 and 2 (C0 lives between them):
+ *   pcr_stats_partial  writes double[9] = sum xyz, min xyz, max xyz of the local shard;
+ *   the caller all-reduces (sum / min / max) and passes the global double[10]
+ *   (mean xyz, min xyz, max xyz, scale) to pcr_standardize_with_stats. */
+int pcr_stats_partial(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols,
+                      double* d_partial9, void* stream);
+int pcr_standardize_with_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols,
+                               const float* d_radius, const float* d_rgb, const pcr_style* style,
+                               const double* d_stats10, float* d_pos_out, float* d_attr_out,
+                               float* d_vel_out, void* stream);
+
+/* Counters of the last pcr_render / pcr_render_frames call (synchronises `stream`):
+ * out[0] = kernels launched, out[1] = (tile,sphere) pairs of the last frame,
+ * out[2] = frames that overflowed pair_capacity, out[3] = spheres culled (last frame). */
+int pcr_counters(pcr_ctx* ctx, int64_t out[4], void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCR_H_ */
