@@ -93,7 +93,9 @@ typedef struct pcr_style {
     float light_half;
     float radiance;
     float bounce;        /* weight of the ground-bounce term on spheres (1.0)     */
-    float reserved;
+    int32_t xform;       /* 0: the reference's axis transform (permute, flip, lift);
+                            1: none (standardise only) — lets the facade expose
+                            standardize_point_cloud / transform_coordinates separately */
 } pcr_style;
 
 /* f32 camera frame derived on the HOST in double precision from a pcr_camera.

@@ -1,0 +1,278 @@
+"""ctypes binding of libpcr.so — the C ABI declared in include/pcr.h.
+
+There is no CPU or PyTorch fallback: if the extension is missing or no CUDA device is
+present, the calls raise.  torch is used only for device memory and streams.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpcr.so")
+
+ID_FLOOR = 0xFFFFFFFE
+ID_MISS = 0xFFFFFFFF
+KEY_MISS = 0x7F800000FFFFFFFF
+
+COLOR_CONST, COLOR_POSITION, COLOR_VELOCITY, COLOR_USER = 0, 1, 2, 3
+
+# every symbol include/pcr.h declares (tests check the library exports all of them)
+SYMBOLS = (
+    "pcr_abi_version", "pcr_create", "pcr_destroy", "pcr_last_error", "pcr_camera_frame",
+    "pcr_standardize", "pcr_render", "pcr_shade", "pcr_render_frames", "pcr_render_frames_host",
+    "pcr_zmin", "pcr_zmerge_nccl", "pcr_stats_partial", "pcr_standardize_with_stats", "pcr_counters",
+)
+
+
+class Camera(ctypes.Structure):
+    """pcr_camera — the <sensor> block of XMLTemplates.HEAD (example_renderer.py:16-31)."""
+    _fields_ = [("origin", ctypes.c_float * 3), ("target", ctypes.c_float * 3), ("up", ctypes.c_float * 3),
+                ("fov_x_deg", ctypes.c_float), ("near_clip", ctypes.c_float), ("far_clip", ctypes.c_float),
+                ("width", ctypes.c_int32), ("height", ctypes.c_int32)]
+
+
+class Style(ctypes.Structure):
+    """pcr_style — BALL_SEGMENT / TAIL constants (example_renderer.py:41-72) + transform flavour."""
+    _fields_ = [("color_mode", ctypes.c_int32), ("const_rgb", ctypes.c_float * 3), ("radius", ctypes.c_float),
+                ("flip_x", ctypes.c_int32), ("z_lift", ctypes.c_float), ("vel_norm", ctypes.c_float),
+                ("has_floor", ctypes.c_int32), ("floor_z", ctypes.c_float), ("floor_min", ctypes.c_float * 2),
+                ("floor_max", ctypes.c_float * 2), ("floor_albedo", ctypes.c_float), ("light_z", ctypes.c_float),
+                ("light_half", ctypes.c_float), ("radiance", ctypes.c_float), ("bounce", ctypes.c_float),
+                ("xform", ctypes.c_int32)]
+
+
+class Frame(ctypes.Structure):
+    """pcr_frame — derived f32 camera frame."""
+    _fields_ = [("L", ctypes.c_float * 3), ("U", ctypes.c_float * 3), ("D", ctypes.c_float * 3),
+                ("O", ctypes.c_float * 3), ("T", ctypes.c_float), ("Th", ctypes.c_float), ("TW", ctypes.c_float),
+                ("near_clip", ctypes.c_float), ("far_clip", ctypes.c_float), ("W", ctypes.c_int32), ("H", ctypes.c_int32)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libpcr.so and declare the prototypes.  Raises if the extension was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -m pointcloud_render_b200.build` "
+            "(there is no CPU fallback for the render path)")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i64, i32, u32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_uint32
+    camp, styp = ctypes.POINTER(Camera), ctypes.POINTER(Style)
+    L.pcr_abi_version.restype = i32
+    L.pcr_create.argtypes = [ctypes.POINTER(vp), i32, i64, i32, i32, i32, i64]
+    L.pcr_destroy.argtypes = [vp]
+    L.pcr_destroy.restype = None
+    L.pcr_last_error.argtypes = [vp]
+    L.pcr_last_error.restype = ctypes.c_char_p
+    L.pcr_camera_frame.argtypes = [camp, ctypes.POINTER(Frame)]
+    L.pcr_standardize.argtypes = [vp, vp, i32, i64, i32, vp, vp, styp, vp, vp, vp, vp, vp]
+    L.pcr_render.argtypes = [vp, vp, vp, i64, u32, camp, styp, vp, vp, vp]
+    L.pcr_shade.argtypes = [vp, vp, vp, vp, i64, u32, i32, camp, styp, vp, vp]
+    L.pcr_render_frames.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, camp, styp, vp, vp, vp]
+    L.pcr_render_frames_host.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, camp, styp, vp, vp]
+    L.pcr_zmin.argtypes = [vp, vp, vp, i64, vp]
+    L.pcr_zmerge_nccl.argtypes = [vp, vp, i64, vp, vp]
+    L.pcr_stats_partial.argtypes = [vp, vp, i32, i64, i32, vp, vp]
+    L.pcr_standardize_with_stats.argtypes = [vp, vp, i32, i64, i32, vp, vp, styp, vp, vp, vp, vp, vp]
+    L.pcr_counters.argtypes = [vp, ctypes.POINTER(i64), vp]
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if name not in ("pcr_destroy", "pcr_last_error"):
+            fn.restype = i32
+    _lib = L
+    return L
+
+
+def make_camera(origin, target, up=(0.0, 0.0, 1.0), fov_x_deg=30.0, near_clip=0.1, far_clip=100.0,
+                width=1920, height=1080):
+    c = Camera()
+    c.origin = (ctypes.c_float * 3)(*[float(x) for x in origin])
+    c.target = (ctypes.c_float * 3)(*[float(x) for x in target])
+    c.up = (ctypes.c_float * 3)(*[float(x) for x in up])
+    c.fov_x_deg, c.near_clip, c.far_clip = float(fov_x_deg), float(near_clip), float(far_clip)
+    c.width, c.height = int(width), int(height)
+    return c
+
+
+def make_style(color_mode=COLOR_CONST, const_rgb=(0.3, 0.3, 0.3), radius=0.01, flip_x=True, z_lift=0.0125,
+               vel_norm=10.0, has_floor=True, floor_z=-0.2, floor_min=(-10.0, -10.0), floor_max=(10.0, 10.0),
+               floor_albedo=1.0, light_z=15.0, light_half=8.0, radiance=4.0, bounce=1.0, xform=0):
+    s = Style()
+    s.color_mode = int(color_mode)
+    s.const_rgb = (ctypes.c_float * 3)(*const_rgb)
+    s.radius, s.flip_x, s.z_lift, s.vel_norm = float(radius), int(bool(flip_x)), float(z_lift), float(vel_norm)
+    s.has_floor, s.floor_z = int(bool(has_floor)), float(floor_z)
+    s.floor_min = (ctypes.c_float * 2)(*floor_min)
+    s.floor_max = (ctypes.c_float * 2)(*floor_max)
+    s.floor_albedo, s.light_z, s.light_half = float(floor_albedo), float(light_z), float(light_half)
+    s.radiance, s.bounce, s.xform = float(radiance), float(bounce), int(xform)
+    return s
+
+
+def camera_frame(cam):
+    f = Frame()
+    rc = load_library().pcr_camera_frame(ctypes.byref(cam), ctypes.byref(f))
+    if rc != 0:
+        raise ValueError("degenerate camera")
+    return f
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(stream):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+class Context:
+    """Owns one pcr_ctx (scratch for one GPU).  Arguments are torch CUDA tensors."""
+
+    def __init__(self, device=0, max_points=1 << 20, max_w=1920, max_h=1080, max_batch=1, pair_capacity=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("pcr needs a CUDA device (no CPU fallback)")
+        self.lib = load_library()
+        self.device = int(device)
+        self.max_points, self.max_w, self.max_h, self.max_batch = int(max_points), int(max_w), int(max_h), int(max_batch)
+        h = ctypes.c_void_p()
+        rc = self.lib.pcr_create(ctypes.byref(h), self.device, self.max_points, self.max_w, self.max_h, self.max_batch,
+                                 int(pair_capacity))
+        if rc != 0:
+            raise RuntimeError(f"pcr_create failed with status {rc}")
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.pcr_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.pcr_last_error(self.handle)
+            raise RuntimeError(f"pcr error {rc}: {msg.decode() if msg else ''}")
+
+    # ---- K0 + K1 -------------------------------------------------------------------------
+    def standardize(self, pts, style, radius=None, rgb=None, want_vel=False, want_stats=False, stream=None):
+        """pts: (N,3|6) float32/float64 CUDA tensor -> pos4 (N,4), attr4 (N,4)[, vel4][, stats(10)]."""
+        import torch
+        assert pts.is_cuda and pts.is_contiguous() and pts.dim() == 2
+        n, cols = pts.shape
+        is64 = pts.dtype == torch.float64
+        assert is64 or pts.dtype == torch.float32
+        dev = pts.device
+        pos = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        attr = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        vel = torch.empty((n, 4), dtype=torch.float32, device=dev) if (want_vel and cols == 6) else None
+        stats = torch.empty(10, dtype=torch.float64, device=dev) if want_stats else None
+        self._check(self.lib.pcr_standardize(self.handle, _ptr(pts), int(is64), n, cols, _ptr(radius), _ptr(rgb),
+                                             ctypes.byref(style), _ptr(pos), _ptr(attr), _ptr(vel), _ptr(stats),
+                                             _stream_ptr(stream)))
+        out = [pos, attr]
+        if want_vel:
+            out.append(vel)
+        if want_stats:
+            out.append(stats)
+        return tuple(out)
+
+    def stats_partial(self, pts, stream=None):
+        import torch
+        n, cols = pts.shape
+        out = torch.empty(10, dtype=torch.float64, device=pts.device)
+        self._check(self.lib.pcr_stats_partial(self.handle, _ptr(pts), int(pts.dtype == torch.float64), n, cols,
+                                               _ptr(out), _stream_ptr(stream)))
+        return out[:9]
+
+    def standardize_with_stats(self, pts, style, stats10, radius=None, rgb=None, stream=None):
+        import torch
+        n, cols = pts.shape
+        pos = torch.empty((n, 4), dtype=torch.float32, device=pts.device)
+        attr = torch.empty((n, 4), dtype=torch.float32, device=pts.device)
+        self._check(self.lib.pcr_standardize_with_stats(self.handle, _ptr(pts), int(pts.dtype == torch.float64), n, cols,
+                                                        _ptr(radius), _ptr(rgb), ctypes.byref(style), _ptr(stats10),
+                                                        _ptr(pos), _ptr(attr), None, _stream_ptr(stream)))
+        return pos, attr
+
+    # ---- K2..K4 ----------------------------------------------------------------------------
+    def render(self, pos4, attr4, cam, style, id_base=0, shade=True, stream=None):
+        """pos4/attr4: (N,4) float32 CUDA -> vis (H,W) int64 view of the uint64 keys, rgba (H,W,4) uint8."""
+        import torch
+        n = pos4.shape[0]
+        dev = pos4.device
+        vis = torch.empty((cam.height, cam.width), dtype=torch.int64, device=dev)
+        rgba = torch.empty((cam.height, cam.width, 4), dtype=torch.uint8, device=dev) if shade else None
+        self._check(self.lib.pcr_render(self.handle, _ptr(pos4) if n else None, _ptr(attr4) if n else None, n, int(id_base),
+                                        ctypes.byref(cam), ctypes.byref(style), _ptr(vis), _ptr(rgba), _stream_ptr(stream)))
+        return vis, rgba
+
+    def shade(self, vis, pos4, attr4, cam, style, id_base=0, owner_only=False, stream=None):
+        import torch
+        rgba = torch.empty((cam.height, cam.width, 4), dtype=torch.uint8, device=vis.device)
+        n = pos4.shape[0]
+        self._check(self.lib.pcr_shade(self.handle, _ptr(vis), _ptr(pos4) if n else None, _ptr(attr4) if n else None, n,
+                                       int(id_base), int(owner_only), ctypes.byref(cam), ctypes.byref(style), _ptr(rgba),
+                                       _stream_ptr(stream)))
+        return rgba
+
+    def render_frames(self, traj, cams, style, radius=None, rgb=None, want_vis=False, out_rgba=None, out_vis=None,
+                      stream=None):
+        """traj: (F,N,3|6) CUDA tensor; cams: list of Camera -> rgba (F,H,W,4) uint8 [, vis (F,H,W) int64]."""
+        import torch
+        assert traj.is_cuda and traj.is_contiguous() and traj.dim() == 3
+        F, n, cols = traj.shape
+        assert len(cams) == F
+        W, H = cams[0].width, cams[0].height
+        cam_arr = (Camera * F)(*cams)
+        rgba = out_rgba if out_rgba is not None else torch.empty((F, H, W, 4), dtype=torch.uint8, device=traj.device)
+        vis = out_vis if out_vis is not None else (
+            torch.empty((F, H, W), dtype=torch.int64, device=traj.device) if want_vis else None)
+        self._check(self.lib.pcr_render_frames(self.handle, _ptr(traj), int(traj.dtype == torch.float64), n, cols, F,
+                                               _ptr(radius), _ptr(rgb), cam_arr, ctypes.byref(style), _ptr(vis),
+                                               _ptr(rgba), _stream_ptr(stream)))
+        return (rgba, vis) if (want_vis or out_vis is not None) else rgba
+
+    def render_frames_host(self, traj_host, cams, style, radius_host=None, rgb_host=None, out_rgba=None, out_vis=None):
+        """Host-buffer entry (what a reference script would call): traj_host is a CPU tensor or
+        numpy array (F,N,3|6), ideally pinned; returns rgba as a CPU tensor (F,H,W,4).  Synchronous."""
+        import torch
+        t = torch.as_tensor(traj_host)
+        assert not t.is_cuda and t.is_contiguous() and t.dim() == 3
+        F, n, cols = t.shape
+        W, H = cams[0].width, cams[0].height
+        cam_arr = (Camera * F)(*cams)
+        rgba = out_rgba if out_rgba is not None else torch.empty((F, H, W, 4), dtype=torch.uint8).pin_memory()
+        hp = lambda x: None if x is None else ctypes.c_void_p(torch.as_tensor(x).data_ptr())
+        self._check(self.lib.pcr_render_frames_host(self.handle, hp(t), int(t.dtype == torch.float64), n, cols, F,
+                                                    hp(radius_host), hp(rgb_host), cam_arr, ctypes.byref(style),
+                                                    hp(out_vis), hp(rgba)))
+        return rgba
+
+    # ---- merge ---------------------------------------------------------------------------
+    def zmin_(self, dst, src, stream=None):
+        self._check(self.lib.pcr_zmin(self.handle, _ptr(dst), _ptr(src), dst.numel(), _stream_ptr(stream)))
+        return dst
+
+    def counters(self, stream=None):
+        out = (ctypes.c_int64 * 4)()
+        self._check(self.lib.pcr_counters(self.handle, out, _stream_ptr(stream)))
+        return {"launches": out[0], "pairs_last_frame": out[1], "overflow_frames": out[2]}
+
+
+def keys_to_ids(vis):
+    """Low 32 bits of the keys as uint32 numpy array."""
+    a = vis.cpu().numpy() if hasattr(vis, "cpu") else np.asarray(vis)
+    return (a.view(np.uint64) & np.uint64(0xFFFFFFFF)).astype(np.uint32)

@@ -1,0 +1,554 @@
+// pcr_api.cu — host side of the C ABI declared in include/pcr.h.
+// Replaces the reference's generate_xml_content -> save_xml -> mi.load_file -> mi.render ->
+// write_bitmap(sRGB8) chain (example_renderer.py:113-161) with stream-ordered kernel launches.
+#include "pcr.h"
+#include "pcr_kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace pcr;
+
+namespace {
+
+constexpr int RING_SLOTS = 4;
+constexpr int MAX_STAT_BLOCKS = 1184;   // 148 SMs x 8
+
+}  // namespace
+
+struct pcr_ctx {
+    int device = 0;
+    long long max_points = 0;
+    int max_w = 0, max_h = 0, max_batch = 1;
+    long long pair_cap = 0;
+    int tiles_cap = 0;
+    int num_sms = 148;
+    std::string err;
+    long long launches = 0;
+
+    // scratch, all [max_batch][...]
+    float4 *pos = nullptr, *attr = nullptr, *sph = nullptr;
+    ushort4* rect = nullptr;
+    double *partials = nullptr, *stats = nullptr;
+    unsigned int* done = nullptr;
+    unsigned int *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *pairs = nullptr, *overflow = nullptr;
+    unsigned long long* stat_pairs = nullptr;
+    uint64_t* vis = nullptr;          // lazily allocated when the caller passes d_vis == NULL
+    FrameDev* d_frames = nullptr;
+    FrameDev* h_frames = nullptr;     // pinned ring: RING_SLOTS x max_batch
+    cudaEvent_t ring_ev[RING_SLOTS] = {};
+    bool ring_used[RING_SLOTS] = {};
+    int ring_next = 0;
+
+    // host-buffer pipeline (pcr_render_frames_host), lazily created
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
+    void* stage_in[2] = {nullptr, nullptr};
+    uint8_t* stage_rgba[2] = {nullptr, nullptr};
+    uint64_t* stage_vis[2] = {nullptr, nullptr};
+    size_t stage_in_bytes = 0;
+    float *stage_radius = nullptr, *stage_rgb = nullptr;
+
+    long long last_overflow_frames = 0;
+};
+
+namespace {
+
+int fail(pcr_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess)
+{
+    if (c) {
+        c->err = what;
+        if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
+    }
+    return code;
+}
+
+#define CK(call)                                                            \
+    do {                                                                    \
+        cudaError_t e_ = (call);                                            \
+        if (e_ != cudaSuccess) return fail(ctx, PCR_ERR_CUDA, #call, e_);   \
+    } while (0)
+
+#define CKL(name)                                                           \
+    do {                                                                    \
+        cudaError_t e_ = cudaGetLastError();                                \
+        if (e_ != cudaSuccess) return fail(ctx, PCR_ERR_CUDA, name, e_);    \
+        ctx->launches++;                                                    \
+    } while (0)
+
+StyleDev to_style_dev(const pcr_style* s)
+{
+    StyleDev d;
+    d.color_mode = s->color_mode;
+    for (int k = 0; k < 3; ++k) d.const_rgb[k] = s->const_rgb[k];
+    d.radius = s->radius; d.flip_x = s->flip_x; d.z_lift = s->z_lift; d.vel_norm = s->vel_norm;
+    d.has_floor = s->has_floor; d.floor_z = s->floor_z;
+    for (int k = 0; k < 2; ++k) { d.floor_min[k] = s->floor_min[k]; d.floor_max[k] = s->floor_max[k]; }
+    d.floor_albedo = s->floor_albedo; d.light_z = s->light_z; d.light_half = s->light_half;
+    d.radiance = s->radiance; d.bounce = s->bounce; d.xform = s->xform;
+    return d;
+}
+
+// Camera frame in double on the host, rounded once to f32.  Mitsuba 3 look_at /
+// perspective conventions for the <sensor> block of XMLTemplates.HEAD (example_renderer.py:16-31).
+int camera_frame_host(const pcr_camera* cam, pcr_frame* f)
+{
+    if (!cam || !f || cam->width <= 0 || cam->height <= 0) return PCR_ERR_INVALID;
+    double o[3], d[3], u[3], l[3], nu[3];
+    for (int k = 0; k < 3; ++k) { o[k] = cam->origin[k]; d[k] = (double)cam->target[k] - (double)cam->origin[k]; u[k] = cam->up[k]; }
+    double len = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    if (!(len > 0.0)) return PCR_ERR_INVALID;
+    for (int k = 0; k < 3; ++k) d[k] = d[k] / len;
+    l[0] = u[1] * d[2] - u[2] * d[1];
+    l[1] = u[2] * d[0] - u[0] * d[2];
+    l[2] = u[0] * d[1] - u[1] * d[0];
+    len = sqrt(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]);
+    if (!(len > 0.0)) return PCR_ERR_INVALID;
+    for (int k = 0; k < 3; ++k) l[k] = l[k] / len;
+    nu[0] = d[1] * l[2] - d[2] * l[1];
+    nu[1] = d[2] * l[0] - d[0] * l[2];
+    nu[2] = d[0] * l[1] - d[1] * l[0];
+    double T = tan((double)cam->fov_x_deg * 3.14159265358979323846 / 360.0);
+    for (int k = 0; k < 3; ++k) { f->L[k] = (float)l[k]; f->U[k] = (float)nu[k]; f->D[k] = (float)d[k]; f->O[k] = (float)o[k]; }
+    f->T = (float)T;
+    f->Th = (float)(T * (double)cam->height / (double)cam->width);
+    f->TW = (float)(T / (double)cam->width);
+    f->near_clip = cam->near_clip; f->far_clip = cam->far_clip;
+    f->W = cam->width; f->H = cam->height;
+    return PCR_OK;
+}
+
+void to_frame_dev(const pcr_frame& f, FrameDev* d)
+{
+    for (int k = 0; k < 3; ++k) { d->L[k] = f.L[k]; d->U[k] = f.U[k]; d->D[k] = f.D[k]; d->O[k] = f.O[k]; }
+    d->T = f.T; d->Th = f.Th; d->TW = f.TW; d->inv2TW = 1.0f / (2.0f * f.TW);
+    d->near_clip = f.near_clip; d->far_clip = f.far_clip;
+    d->W = f.W; d->H = f.H;
+    d->tiles_x = (f.W + TILE - 1) / TILE; d->tiles_y = (f.H + TILE - 1) / TILE;
+}
+
+BinDev bin_of(pcr_ctx* c)
+{
+    BinDev b;
+    b.counts = c->counts; b.offsets = c->offsets; b.cursor = c->cursor; b.pairs = c->pairs;
+    b.overflow = c->overflow; b.stat_pairs = c->stat_pairs; b.tiles_cap = c->tiles_cap; b.pair_cap = c->pair_cap;
+    return b;
+}
+
+// Upload `nb` cameras into d_frames through the pinned ring.
+int upload_frames(pcr_ctx* ctx, const pcr_camera* cams, int nb, cudaStream_t stream)
+{
+    int slot = ctx->ring_next;
+    ctx->ring_next = (slot + 1) % RING_SLOTS;
+    if (ctx->ring_used[slot]) CK(cudaEventSynchronize(ctx->ring_ev[slot]));
+    FrameDev* h = ctx->h_frames + (size_t)slot * ctx->max_batch;
+    for (int b = 0; b < nb; ++b) {
+        pcr_frame f;
+        if (camera_frame_host(cams + b, &f) != PCR_OK) return fail(ctx, PCR_ERR_INVALID, "degenerate camera");
+        if (f.W > ctx->max_w || f.H > ctx->max_h) return fail(ctx, PCR_ERR_CAPACITY, "frame larger than the context");
+        to_frame_dev(f, h + b);
+    }
+    CK(cudaMemcpyAsync(ctx->d_frames, h, sizeof(FrameDev) * nb, cudaMemcpyHostToDevice, stream));
+    CK(cudaEventRecord(ctx->ring_ev[slot], stream));
+    ctx->ring_used[slot] = true;
+    return PCR_OK;
+}
+
+int launch_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, long long n, int cols, long long frame_stride,
+                 int nb, double* partials, double* stats, int finalize, cudaStream_t stream)
+{
+    int blocks = (int)std::min<long long>((n + 256 * 8 - 1) / (256 * 8), MAX_STAT_BLOCKS);
+    blocks = std::max(blocks, 1);
+    dim3 grid(blocks, nb);
+    if (in_is_f64)
+        k_stats<double><<<grid, 256, 0, stream>>>((const double*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, ctx->done, finalize);
+    else
+        k_stats<float><<<grid, 256, 0, stream>>>((const float*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, ctx->done, finalize);
+    CKL("k_stats");
+    return PCR_OK;
+}
+
+int launch_transform(pcr_ctx* ctx, const void* d_in, int in_is_f64, long long n, int cols, long long frame_stride,
+                     int nb, const float* d_radius, const float* d_rgb, const double* stats, const StyleDev& st,
+                     float4* pos, float4* attr, float4* vel, long long out_stride, cudaStream_t stream)
+{
+    dim3 grid((unsigned)((n + 255) / 256), nb);
+    if (in_is_f64)
+        k_transform<double><<<grid, 256, 0, stream>>>((const double*)d_in, n, cols, frame_stride, d_radius, d_rgb, stats, st, pos, attr, vel, out_stride);
+    else
+        k_transform<float><<<grid, 256, 0, stream>>>((const float*)d_in, n, cols, frame_stride, d_radius, d_rgb, stats, st, pos, attr, vel, out_stride);
+    CKL("k_transform");
+    return PCR_OK;
+}
+
+// K2a -> scan -> K2b -> K3 (-> fallback) (-> K4) for nb frames whose cameras are already in d_frames.
+int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long in_stride, long long n, int nb,
+                  uint32_t id_base, const StyleDev& st, int W, int H, uint64_t* vis, long long vis_stride,
+                  uint8_t* rgba, long long rgba_stride, int owner_only, cudaStream_t stream)
+{
+    BinDev bin = bin_of(ctx);
+    const int tiles = ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    if (n > 0) {
+        dim3 grid((unsigned)((n + 255) / 256), nb);
+        k_project_count<<<grid, 256, 0, stream>>>(pos, n, in_stride, ctx->d_frames, ctx->sph, ctx->rect, ctx->max_points, bin);
+        CKL("k_project_count");
+    }
+    k_scan_tiles<<<nb, 1024, 0, stream>>>(ctx->d_frames, bin);
+    CKL("k_scan_tiles");
+    if (n > 0) {
+        dim3 grid((unsigned)((n + 255) / 256), nb);
+        k_scatter<<<grid, 256, 0, stream>>>(n, ctx->d_frames, ctx->rect, ctx->max_points, bin);
+        CKL("k_scatter");
+    }
+    {
+        dim3 grid(tiles, nb);
+        k_raster_tiles<<<grid, RASTER_THREADS, 0, stream>>>(ctx->d_frames, st, ctx->sph, ctx->rect, ctx->max_points, bin, id_base, vis, vis_stride);
+        CKL("k_raster_tiles");
+    }
+    if (n > 0) {
+        dim3 grid(ctx->num_sms * 4, nb);
+        k_raster_naive<<<grid, 256, 0, stream>>>(n, ctx->d_frames, ctx->sph, ctx->rect, ctx->max_points, bin, id_base,
+                                                 (unsigned long long*)vis, vis_stride);
+        CKL("k_raster_naive");
+    }
+    if (rgba) {
+        dim3 grid((unsigned)(((long long)W * H + 255) / 256), nb);
+        k_shade<<<grid, 256, 0, stream>>>(ctx->d_frames, st, vis, vis_stride, pos, attr, in_stride, n, id_base, owner_only,
+                                          (uint32_t*)rgba, rgba_stride);
+        CKL("k_shade");
+    }
+    return PCR_OK;
+}
+
+int check_common(pcr_ctx* ctx, long long n, int cols, const pcr_style* style)
+{
+    if (!ctx) return PCR_ERR_INVALID;
+    if (!style) return fail(ctx, PCR_ERR_INVALID, "style is NULL");
+    if (n < 0 || (cols != 3 && cols != 6)) return fail(ctx, PCR_ERR_INVALID, "n < 0 or cols not 3|6");
+    if (n > ctx->max_points) return fail(ctx, PCR_ERR_CAPACITY, "n exceeds the context's max_points");
+    return PCR_OK;
+}
+
+int ensure_vis(pcr_ctx* ctx)
+{
+    if (!ctx->vis) CK(cudaMalloc(&ctx->vis, sizeof(uint64_t) * (size_t)ctx->max_batch * ctx->max_w * ctx->max_h));
+    return PCR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pcr_abi_version(void) { return PCR_ABI_VERSION; }
+
+const char* pcr_last_error(const pcr_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int pcr_camera_frame(const pcr_camera* cam, pcr_frame* out) { return camera_frame_host(cam, out); }
+
+int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max_h, int max_batch, int64_t pair_capacity)
+{
+    if (!out || max_points < 1 || max_points > 0xFFFFFFF0ll || max_w < 1 || max_h < 1 || max_w > 65535 || max_h > 65535 || max_batch < 1)
+        return PCR_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return PCR_ERR_CUDA;
+    pcr_ctx* ctx = new (std::nothrow) pcr_ctx();
+    if (!ctx) return PCR_ERR_NOMEM;
+    ctx->device = device; ctx->max_points = max_points; ctx->max_w = max_w; ctx->max_h = max_h; ctx->max_batch = max_batch;
+    ctx->pair_cap = pair_capacity > 0 ? pair_capacity : 8 * max_points + 65536;
+    if (ctx->pair_cap > 0xFFFFFFF0ll) ctx->pair_cap = 0xFFFFFFF0ll;
+    ctx->tiles_cap = ((max_w + TILE - 1) / TILE) * ((max_h + TILE - 1) / TILE);
+    const size_t B = (size_t)max_batch, N = (size_t)max_points, Tn = (size_t)ctx->tiles_cap;
+    cudaError_t e = cudaSetDevice(device);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
+#define ALLOC(ptr, bytes) if (e == cudaSuccess) e = cudaMalloc((void**)&(ptr), (bytes))
+    ALLOC(ctx->pos, sizeof(float4) * B * N);
+    ALLOC(ctx->attr, sizeof(float4) * B * N);
+    ALLOC(ctx->sph, sizeof(float4) * B * N);
+    ALLOC(ctx->rect, sizeof(ushort4) * B * N);
+    ALLOC(ctx->partials, sizeof(double) * B * MAX_STAT_BLOCKS * 9);
+    ALLOC(ctx->stats, sizeof(double) * B * 10);
+    ALLOC(ctx->done, sizeof(unsigned int) * B);
+    ALLOC(ctx->counts, sizeof(unsigned int) * B * Tn);
+    ALLOC(ctx->offsets, sizeof(unsigned int) * B * (Tn + 1));
+    ALLOC(ctx->cursor, sizeof(unsigned int) * B * Tn);
+    ALLOC(ctx->pairs, sizeof(unsigned int) * B * (size_t)ctx->pair_cap);
+    ALLOC(ctx->overflow, sizeof(unsigned int) * B);
+    ALLOC(ctx->stat_pairs, sizeof(unsigned long long) * B);
+    ALLOC(ctx->d_frames, sizeof(FrameDev) * B);
+#undef ALLOC
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_frames, sizeof(FrameDev) * B * RING_SLOTS);
+    if (e == cudaSuccess) e = cudaMemset(ctx->counts, 0, sizeof(unsigned int) * B * Tn);
+    if (e == cudaSuccess) e = cudaMemset(ctx->done, 0, sizeof(unsigned int) * B);
+    if (e == cudaSuccess) e = cudaMemset(ctx->overflow, 0, sizeof(unsigned int) * B);
+    if (e == cudaSuccess) e = cudaMemset(ctx->stat_pairs, 0, sizeof(unsigned long long) * B);
+    for (int k = 0; k < RING_SLOTS && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&ctx->ring_ev[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        int code = e == cudaErrorMemoryAllocation ? PCR_ERR_NOMEM : PCR_ERR_CUDA;
+        pcr_destroy(ctx);
+        cudaGetLastError();
+        return code;
+    }
+    *out = ctx;
+    return PCR_OK;
+}
+
+void pcr_destroy(pcr_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    void* frees[] = {ctx->pos, ctx->attr, ctx->sph, ctx->rect, ctx->partials, ctx->stats, ctx->done, ctx->counts, ctx->offsets,
+                     ctx->cursor, ctx->pairs, ctx->overflow, ctx->stat_pairs, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
+                     ctx->stage_rgba[0], ctx->stage_rgba[1], ctx->stage_vis[0], ctx->stage_vis[1], ctx->stage_radius, ctx->stage_rgb};
+    for (void* p : frees) if (p) cudaFree(p);
+    if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
+    for (int k = 0; k < RING_SLOTS; ++k) if (ctx->ring_ev[k]) cudaEventDestroy(ctx->ring_ev[k]);
+    for (int k = 0; k < 2; ++k) {
+        if (ctx->ev_h2d[k]) cudaEventDestroy(ctx->ev_h2d[k]);
+        if (ctx->ev_comp[k]) cudaEventDestroy(ctx->ev_comp[k]);
+        if (ctx->ev_d2h[k]) cudaEventDestroy(ctx->ev_d2h[k]);
+    }
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    delete ctx;
+}
+
+int pcr_stats_partial(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols, double* d_partial9, void* stream)
+{
+    pcr_style dummy; memset(&dummy, 0, sizeof(dummy));
+    int rc = check_common(ctx, n, cols, &dummy);
+    if (rc) return rc;
+    if (!d_in || !d_partial9 || n < 1) return fail(ctx, PCR_ERR_INVALID, "pcr_stats_partial: NULL buffer or n < 1");
+    CK(cudaSetDevice(ctx->device));
+    int rc2 = launch_stats(ctx, d_in, in_is_f64, n, cols, 0, 1, ctx->partials, d_partial9, 2, (cudaStream_t)stream);
+    if (rc2) return rc2;
+    return PCR_OK;
+}
+
+int pcr_standardize_with_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols, const float* d_radius,
+                               const float* d_rgb, const pcr_style* style, const double* d_stats10, float* d_pos_out,
+                               float* d_attr_out, float* d_vel_out, void* stream)
+{
+    int rc = check_common(ctx, n, cols, style);
+    if (rc) return rc;
+    if (n == 0) return PCR_OK;
+    if (!d_in || !d_stats10 || !d_pos_out || !d_attr_out) return fail(ctx, PCR_ERR_INVALID, "pcr_standardize: NULL buffer");
+    CK(cudaSetDevice(ctx->device));
+    return launch_transform(ctx, d_in, in_is_f64, n, cols, 0, 1, d_radius, d_rgb, d_stats10, to_style_dev(style),
+                            (float4*)d_pos_out, (float4*)d_attr_out, (float4*)d_vel_out, 0, (cudaStream_t)stream);
+}
+
+int pcr_standardize(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols, const float* d_radius, const float* d_rgb,
+                    const pcr_style* style, float* d_pos_out, float* d_attr_out, float* d_vel_out, double* d_stats, void* stream)
+{
+    int rc = check_common(ctx, n, cols, style);
+    if (rc) return rc;
+    if (n == 0) return PCR_OK;
+    if (!d_in || !d_pos_out || !d_attr_out) return fail(ctx, PCR_ERR_INVALID, "pcr_standardize: NULL buffer");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    rc = launch_stats(ctx, d_in, in_is_f64, n, cols, 0, 1, ctx->partials, ctx->stats, 1, s);
+    if (rc) return rc;
+    rc = launch_transform(ctx, d_in, in_is_f64, n, cols, 0, 1, d_radius, d_rgb, ctx->stats, to_style_dev(style),
+                          (float4*)d_pos_out, (float4*)d_attr_out, (float4*)d_vel_out, 0, s);
+    if (rc) return rc;
+    if (d_stats) CK(cudaMemcpyAsync(d_stats, ctx->stats, sizeof(double) * 10, cudaMemcpyDeviceToDevice, s));
+    return PCR_OK;
+}
+
+int pcr_render(pcr_ctx* ctx, const float* d_pos, const float* d_attr, int64_t n, uint32_t id_base, const pcr_camera* cam,
+               const pcr_style* style, uint64_t* d_vis, uint8_t* d_rgba, void* stream)
+{
+    int rc = check_common(ctx, n, 3, style);
+    if (rc) return rc;
+    if (!cam || !d_vis || (n > 0 && !d_pos) || (d_rgba && n > 0 && !d_attr)) return fail(ctx, PCR_ERR_INVALID, "pcr_render: NULL buffer");
+    if ((unsigned long long)id_base + (unsigned long long)n > 0xFFFFFFFEull) return fail(ctx, PCR_ERR_INVALID, "point id overflow");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    rc = upload_frames(ctx, cam, 1, s);
+    if (rc) return rc;
+    const long long px = (long long)cam->width * cam->height;
+    return launch_render(ctx, (const float4*)d_pos, (const float4*)d_attr, 0, n, 1, id_base, to_style_dev(style), cam->width,
+                         cam->height, d_vis, px, d_rgba, px, 0, s);
+}
+
+int pcr_shade(pcr_ctx* ctx, const uint64_t* d_vis, const float* d_pos, const float* d_attr, int64_t n, uint32_t id_base,
+              int owner_only, const pcr_camera* cam, const pcr_style* style, uint8_t* d_rgba, void* stream)
+{
+    int rc = check_common(ctx, n, 3, style);
+    if (rc) return rc;
+    if (!cam || !d_vis || !d_rgba || (n > 0 && (!d_pos || !d_attr))) return fail(ctx, PCR_ERR_INVALID, "pcr_shade: NULL buffer");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    rc = upload_frames(ctx, cam, 1, s);
+    if (rc) return rc;
+    const long long px = (long long)cam->width * cam->height;
+    dim3 grid((unsigned)((px + 255) / 256), 1);
+    k_shade<<<grid, 256, 0, s>>>(ctx->d_frames, to_style_dev(style), d_vis, px, (const float4*)d_pos, (const float4*)d_attr, 0, n,
+                                 id_base, owner_only, (uint32_t*)d_rgba, px);
+    CKL("k_shade");
+    return PCR_OK;
+}
+
+int pcr_render_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols, int n_frames, const float* d_radius,
+                      const float* d_rgb, const pcr_camera* cams, const pcr_style* style, uint64_t* d_vis, uint8_t* d_rgba,
+                      void* stream)
+{
+    int rc = check_common(ctx, n, cols, style);
+    if (rc) return rc;
+    if (n_frames < 0 || !cams || !d_rgba || (n > 0 && !d_in)) return fail(ctx, PCR_ERR_INVALID, "pcr_render_frames: NULL buffer");
+    if (n < 1) return fail(ctx, PCR_ERR_INVALID, "pcr_render_frames: empty frames cannot be standardised");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const StyleDev st = to_style_dev(style);
+    const int W = cams[0].width, H = cams[0].height;
+    for (int f = 0; f < n_frames; ++f)
+        if (cams[f].width != W || cams[f].height != H) return fail(ctx, PCR_ERR_INVALID, "all frames of a call must share W x H");
+    const long long px = (long long)W * H;
+    const size_t elem = in_is_f64 ? 8 : 4;
+    const long long frame_stride = n * cols;
+    if (!d_vis) { rc = ensure_vis(ctx); if (rc) return rc; }
+    for (int f0 = 0; f0 < n_frames; f0 += ctx->max_batch) {
+        const int nb = std::min(ctx->max_batch, n_frames - f0);
+        rc = upload_frames(ctx, cams + f0, nb, s);
+        if (rc) return rc;
+        const char* in = (const char*)d_in + (size_t)f0 * frame_stride * elem;
+        rc = launch_stats(ctx, in, in_is_f64, n, cols, frame_stride, nb, ctx->partials, ctx->stats, 1, s);
+        if (rc) return rc;
+        rc = launch_transform(ctx, in, in_is_f64, n, cols, frame_stride, nb, d_radius, d_rgb, ctx->stats, st, ctx->pos, ctx->attr,
+                              nullptr, ctx->max_points, s);
+        if (rc) return rc;
+        uint64_t* vis = d_vis ? d_vis + (size_t)f0 * px : ctx->vis;
+        const long long vis_stride = d_vis ? px : (long long)ctx->max_w * ctx->max_h;
+        rc = launch_render(ctx, ctx->pos, ctx->attr, ctx->max_points, n, nb, 0u, st, W, H, vis, vis_stride,
+                           d_rgba + (size_t)f0 * px * 4, px, 0, s);
+        if (rc) return rc;
+    }
+    return PCR_OK;
+}
+
+int pcr_render_frames_host(pcr_ctx* ctx, const void* h_in, int in_is_f64, int64_t n, int cols, int n_frames, const float* h_radius,
+                           const float* h_rgb, const pcr_camera* cams, const pcr_style* style, uint64_t* h_vis, uint8_t* h_rgba)
+{
+    int rc = check_common(ctx, n, cols, style);
+    if (rc) return rc;
+    if (n_frames < 0 || !cams || !h_rgba || !h_in || n < 1) return fail(ctx, PCR_ERR_INVALID, "pcr_render_frames_host: NULL buffer or n < 1");
+    if (n_frames == 0) return PCR_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int W = cams[0].width, H = cams[0].height;
+    if (W > ctx->max_w || H > ctx->max_h) return fail(ctx, PCR_ERR_CAPACITY, "frame larger than the context");
+    const size_t px = (size_t)W * H, elem = in_is_f64 ? 8 : 4;
+    const size_t frame_bytes = (size_t)n * cols * elem;
+    const int B = ctx->max_batch;
+    if (!ctx->s_h2d) {
+        CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            CK(cudaEventCreateWithFlags(&ctx->ev_h2d[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_comp[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_d2h[k], cudaEventDisableTiming));
+            CK(cudaMalloc((void**)&ctx->stage_rgba[k], (size_t)B * ctx->max_w * ctx->max_h * 4));
+            CK(cudaMalloc((void**)&ctx->stage_vis[k], (size_t)B * ctx->max_w * ctx->max_h * 8));
+        }
+        CK(cudaMalloc((void**)&ctx->stage_radius, sizeof(float) * ctx->max_points));
+        CK(cudaMalloc((void**)&ctx->stage_rgb, sizeof(float) * 3 * ctx->max_points));
+    }
+    if (ctx->stage_in_bytes < (size_t)B * frame_bytes) {
+        CK(cudaDeviceSynchronize());
+        for (int k = 0; k < 2; ++k) {
+            if (ctx->stage_in[k]) CK(cudaFree(ctx->stage_in[k]));
+            ctx->stage_in[k] = nullptr;
+            CK(cudaMalloc(&ctx->stage_in[k], (size_t)B * frame_bytes));
+        }
+        ctx->stage_in_bytes = (size_t)B * frame_bytes;
+    }
+    const float *d_radius = nullptr, *d_rgb = nullptr;
+    if (h_radius) { CK(cudaMemcpyAsync(ctx->stage_radius, h_radius, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->s_comp)); d_radius = ctx->stage_radius; }
+    if (h_rgb) { CK(cudaMemcpyAsync(ctx->stage_rgb, h_rgb, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->s_comp)); d_rgb = ctx->stage_rgb; }
+    int chunk = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += B, ++chunk) {
+        const int nb = std::min(B, n_frames - f0);
+        const int k = chunk & 1;
+        if (chunk >= 2) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[k], 0));   // input slot free again
+        CK(cudaMemcpyAsync(ctx->stage_in[k], (const char*)h_in + (size_t)f0 * frame_bytes, (size_t)nb * frame_bytes,
+                           cudaMemcpyHostToDevice, ctx->s_h2d));
+        CK(cudaEventRecord(ctx->ev_h2d[k], ctx->s_h2d));
+        CK(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_h2d[k], 0));
+        if (chunk >= 2) CK(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_d2h[k], 0));  // output slot drained
+        rc = pcr_render_frames(ctx, ctx->stage_in[k], in_is_f64, n, cols, nb, d_radius, d_rgb, cams + f0, style,
+                               ctx->stage_vis[k], ctx->stage_rgba[k], ctx->s_comp);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev_comp[k], ctx->s_comp));
+        CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_comp[k], 0));
+        CK(cudaMemcpyAsync(h_rgba + (size_t)f0 * px * 4, ctx->stage_rgba[k], (size_t)nb * px * 4, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        if (h_vis) CK(cudaMemcpyAsync(h_vis + (size_t)f0 * px, ctx->stage_vis[k], (size_t)nb * px * 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        CK(cudaEventRecord(ctx->ev_d2h[k], ctx->s_d2h));
+    }
+    CK(cudaStreamSynchronize(ctx->s_d2h));
+    CK(cudaStreamSynchronize(ctx->s_comp));
+    return PCR_OK;
+}
+
+int pcr_zmin(pcr_ctx* ctx, uint64_t* d_dst, const uint64_t* d_src, int64_t n_px, void* stream)
+{
+    if (!ctx) return PCR_ERR_INVALID;
+    if (!d_dst || !d_src || n_px < 0) return fail(ctx, PCR_ERR_INVALID, "pcr_zmin: NULL buffer");
+    if (n_px == 0) return PCR_OK;
+    CK(cudaSetDevice(ctx->device));
+    int blocks = (int)std::min<long long>((n_px + 255) / 256, (long long)ctx->num_sms * 16);
+    k_zmin<<<blocks, 256, 0, (cudaStream_t)stream>>>((unsigned long long*)d_dst, (const unsigned long long*)d_src, n_px);
+    CKL("k_zmin");
+    return PCR_OK;
+}
+
+int pcr_zmerge_nccl(pcr_ctx* ctx, uint64_t* d_vis, int64_t n_px, void* comm, void* stream)
+{
+    if (!ctx) return PCR_ERR_INVALID;
+    if (!d_vis || !comm || n_px < 0) return fail(ctx, PCR_ERR_INVALID, "pcr_zmerge_nccl: NULL buffer or communicator");
+    // ncclResult_t ncclAllReduce(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t)
+    typedef int (*allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+    static allreduce_fn fn = nullptr;
+    if (!fn) {
+        fn = (allreduce_fn)dlsym(RTLD_DEFAULT, "ncclAllReduce");
+        if (!fn) {
+            void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (h) fn = (allreduce_fn)dlsym(h, "ncclAllReduce");
+        }
+        if (!fn) return fail(ctx, PCR_ERR_NCCL, "ncclAllReduce not found in this process");
+    }
+    const int kNcclUint64 = 5, kNcclMin = 3;   // nccl.h: ncclUint64 = 5, ncclMin = 3
+    int r = fn(d_vis, d_vis, (size_t)n_px, kNcclUint64, kNcclMin, comm, (cudaStream_t)stream);
+    if (r != 0) return fail(ctx, PCR_ERR_NCCL, "ncclAllReduce(uint64, min) failed");
+    return PCR_OK;
+}
+
+int pcr_counters(pcr_ctx* ctx, int64_t out[4], void* stream)
+{
+    if (!ctx || !out) return PCR_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    unsigned long long pairs = 0;
+    std::vector<unsigned int> ov(ctx->max_batch);
+    CK(cudaMemcpy(&pairs, ctx->stat_pairs, sizeof(pairs), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ov.data(), ctx->overflow, sizeof(unsigned int) * ctx->max_batch, cudaMemcpyDeviceToHost));
+    long long nov = 0;
+    for (unsigned int v : ov) nov += v != 0;
+    out[0] = ctx->launches; out[1] = (int64_t)pairs; out[2] = nov; out[3] = 0;
+    return PCR_OK;
+}
+
+}  // extern "C"
