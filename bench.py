@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of the pcr hot path on BASELINE.json's headline workload.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload H|C2|C3|C4]
+
+Workload H (default): 1 M-point trajectory frames at 1024x1024, `traj_ball` camera schedule.
+A *step* is one pass of the whole hot path (K0 stats, K1 standardise/transform/colour, K2 project +
+tile binning, K3 sphere raster, K4 shade) over one batch of `frames_per_step` frames per GPU.
+
+  value   frames/s over all ranks, inputs resident in HBM (a ring of frames larger than L2)
+  e2e     the same through pcr_render_frames_host: pinned HOST trajectory in, HOST images out,
+          H2D/D2H copies inside the timed region (overlapped with the kernels by the library)
+  roofline  HBM roofline of the dominant kernel (per-kernel CUDA events recorded by the library on
+          its launching stream, over the timed region)
+  cpu_baseline  the CPU oracle (numpy standardise/transform + OpenMP C ray caster + shading) on a
+          bounded sample of the same frames, all host cores.  The reference's real renderer is
+          Mitsuba (absent): the oracle casts 1 ray/pixel where the reference traces 128-256
+          multi-bounce paths, so it is a strict lower bound on the reference's CPU time.
+
+Multi-GPU (torchrun, one rank per GPU): trajectory frames shard across ranks with no collective
+(weak scaling: every rank renders its own frames_per_step frames per step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="H", choices=["H", "C2", "C3", "C4"])
+    ap.add_argument("--frames-per-step", type=int, default=0, help="frames per step per GPU (0 = workload default)")
+    ap.add_argument("--ring", type=int, default=0, help="resident frames per GPU (0 = enough to exceed L2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with events in the timed region")
+    return ap.parse_args()
+
+
+def workload_spec(name, frames_per_step):
+    from pointcloud_render_b200 import synthetic
+    c = dict(synthetic.CONFIGS[name])
+    default_fps = {"H": 8, "C4": 16, "C3": 32, "C2": 32}[name]
+    c["frames_per_step"] = frames_per_step or default_fps
+    b_in = 4 * c["cols"] + (4 if c["radii"] else 0)
+    # input read once, u64 visibility written once, RGBA8 written once
+    c["algorithmic_bytes_per_frame"] = c["points"] * b_in + c["width"] * c["height"] * (8 + 4)
+    c["input_bytes_per_frame"] = c["points"] * 4 * c["cols"]
+    return c
+
+
+def config_dict(name, spec, ring, n_gpus):
+    return {"workload": f"{name}: {spec['points']} points/frame, {spec['width']}x{spec['height']}, preset {spec['preset']}, "
+                        f"{spec['cols']} cols f32, colour mode {spec['color_mode']}" + (", per-point radius" if spec["radii"] else ""),
+            "points": spec["points"], "width": spec["width"], "height": spec["height"],
+            "frames_per_step_per_gpu": spec["frames_per_step"], "resident_ring_frames": ring,
+            "l2_policy": "inputs larger than L2: each step reads a different slice of a resident frame ring "
+                         f"({ring * spec['input_bytes_per_frame'] / 1e6:.0f} MB) and rewrites {spec['frames_per_step'] * spec['width'] * spec['height'] * 12 / 1e6:.0f} MB of outputs",
+            "parallelism": "single GPU" if n_gpus == 1 else f"frames sharded over {n_gpus} GPUs, no collective"}
+
+
+def ring_frames(spec, requested=0):
+    """Resident frames per GPU: a multiple of frames_per_step whose inputs exceed the 126 MB L2."""
+    B = spec["frames_per_step"]
+    ring = requested or max(2 * B, B * int(np.ceil(160e6 / spec["input_bytes_per_frame"] / B)))
+    return (ring + B - 1) // B * B
+
+
+def make_ring(spec, ring, seed):
+    """`ring` frames of the workload's trajectory (camera/physics frame indices 0..ring-1)."""
+    from pointcloud_render_b200 import synthetic
+    return synthetic.trajectory(ring, spec["points"], spec["cols"], "gauss", seed=seed)
+
+
+def cameras_for(spec, first, count):
+    from pointcloud_render_b200.presets import PRESETS
+    total = spec["frames"]
+    cfg = PRESETS[spec["preset"]].for_trajectory(total)
+    return [cfg.camera((first + k) % total, total, spec["width"], spec["height"]) for k in range(count)], cfg
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.samples, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        self.mark0 = self.mark1 = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def begin(self):
+        self.mark0 = time.perf_counter()
+
+    def end(self):
+        self.mark1 = time.perf_counter()
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        if not self.proc or self.mark0 is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi not available"}
+        rows = [s for t, s in self.samples if self.mark0 - 0.05 <= t <= (self.mark1 or t) + 0.05] or [s for _, s in self.samples[-3:]]
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "no samples"}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU side (oracle port) — used for cpu_baseline and for --impl reference only
+def cpu_frame(orc, frame_pts, cfg, cam_index, spec, radius):
+    """One frame of the path on the CPU: numpy standardise + transform + colour hook (reference
+    arithmetic), OpenMP C visibility + shading.  Returns seconds."""
+    t0 = time.perf_counter()
+    p = orc.transform_coordinates(orc.standardize_point_cloud(frame_pts), cfg.flip_x)
+    attr4 = orc.compute_color(p, mode=spec["color_mode"], const_rgb=cfg.const_rgb, vel_norm=cfg.vel_norm)
+    r = radius if radius is not None else np.full(len(p), cfg.radius, np.float32)
+    pos4 = np.concatenate([p[:, :3], r[:, None]], axis=1)
+    fr = orc.camera_frame(cfg.camera_position(cam_index, spec["frames"]), cfg.target, cfg.up, cfg.fov, cfg.near_clip, cfg.far_clip,
+                          spec["width"], spec["height"])
+    sc = orc.make_scene(True, cfg.floor_z, cfg.floor_min, cfg.floor_max, cfg.floor_albedo, cfg.light_z, cfg.light_half,
+                        cfg.radiance, cfg.bounce)
+    vis = orc.visibility(pos4, fr, sc)
+    orc.shade(vis, pos4, attr4, fr, sc)
+    return time.perf_counter() - t0
+
+
+def xml_emit_seconds_per_point(n=20000):
+    """Cost of the reference's per-point XML string loop (example_renderer.py:113-128), restated:
+    reported beside the baseline, NOT included in it."""
+    seg = ('<shape type="sphere"><float name="radius" value="0.01"/><transform name="toWorld"><translate x="{}" y="{}" z="{}"/>'
+           '</transform><bsdf type="diffuse"><rgb name="reflectance" value="{},{},{}"/></bsdf></shape>')
+    pcl = np.random.default_rng(0).standard_normal((n, 3)).astype(np.float32)
+    lo, rng = pcl.min(0), pcl.max(0) - pcl.min(0)
+    t0 = time.perf_counter()
+    out = []
+    for idx, point in enumerate(pcl):
+        q = (point - lo) / (rng + 1e-8)
+        color = np.array([0.3, 0.3, 0.3]) if q[0] > -1 else None
+        out.append(seg.format(point[0], point[1], point[2], *color))
+    "".join(out)
+    return (time.perf_counter() - t0) / n
+
+
+def cpu_baseline(spec, ring_host, radius, budget_s=12.0, max_frames=40):
+    from oracle import pcr_oracle as orc
+    from pointcloud_render_b200.presets import PRESETS
+    cfg = PRESETS[spec["preset"]].for_trajectory(spec["frames"])
+    cpu_frame(orc, ring_host[0], cfg, 0, spec, radius)          # warm-up (page in, OpenMP pool)
+    total, frames = 0.0, 0
+    while frames < max_frames and total < budget_s:
+        total += cpu_frame(orc, ring_host[frames % len(ring_host)], cfg, frames % spec["frames"], spec, radius)
+        frames += 1
+    per_pt = xml_emit_seconds_per_point()
+    return {"value": frames / total, "unit": "frames/s", "cores": orc.num_threads(), "kind": "port",
+            "sample": f"{frames} frames of the same workload ({total:.1f} s): numpy standardise+transform, OpenMP C ray caster 1 ray/pixel + shading",
+            "host_cpus": os.cpu_count(),
+            "note": "lower bound on the reference: Mitsuba (absent) traces 128-256 spp multi-bounce paths; the per-point XML emit loop "
+                    f"of the reference (example_renderer.py:113-128) would add ~{per_pt * spec['points']:.1f} s/frame at this size "
+                    f"({per_pt * 1e6:.1f} us/point measured on 20000 points) and is NOT included"}
+
+
+def run_reference(args, spec, rank, world):
+    """--impl reference: the CPU path, all host threads, each step a bounded sample of the workload."""
+    if rank != 0:
+        return
+    from oracle import pcr_oracle as orc
+    from pointcloud_render_b200.presets import PRESETS
+    orc.build()
+    cfg = PRESETS[spec["preset"]].for_trajectory(spec["frames"])
+    frames_per_step = 2 if spec["points"] >= 500_000 else 4
+    ring = max(4, frames_per_step * 2)
+    host = make_ring(spec, ring, seed=0)
+    from pointcloud_render_b200 import synthetic
+    radius = synthetic.radii(spec["points"]) if spec["radii"] else None
+    k = 0
+    for _ in range(args.warmup):
+        for _ in range(frames_per_step):
+            cpu_frame(orc, host[k % ring], cfg, k % spec["frames"], spec, radius); k += 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(frames_per_step):
+            cpu_frame(orc, host[k % ring], cfg, k % spec["frames"], spec, radius); k += 1
+    dt = time.perf_counter() - t0
+    fps = args.steps * frames_per_step / dt
+    sample = f"{frames_per_step} frames per step of the same workload, oracle port (numpy + OpenMP C ray caster, 1 ray/pixel)"
+    line = {"impl": "reference", "metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "mpoints_per_s": fps * spec["points"] / 1e6,
+            "config": dict(config_dict(args.workload, spec, ring_frames(spec, args.ring), args.gpus),
+                           reference_sample=f"{frames_per_step} frames per step on the host cores"),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": orc.num_threads(), "kind": "port", "sample": sample,
+                             "host_cpus": os.cpu_count()},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    spec = workload_spec(args.workload, args.frames_per_step)
+
+    if args.impl == "reference":
+        run_reference(args, spec, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pointcloud_render_b200 import _native, synthetic
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B = spec["frames_per_step"]
+    ring = ring_frames(spec, args.ring)
+    W, H, n = spec["width"], spec["height"], spec["points"]
+
+    host_np = make_ring(spec, ring, seed=rank)                     # every rank renders its own frames
+    host = torch.from_numpy(host_np).pin_memory()
+    resident = host.cuda(non_blocking=True)
+    radius_np = synthetic.radii(n) if spec["radii"] else None
+    radius = torch.from_numpy(radius_np).cuda() if radius_np is not None else None
+    ctx = _native.Context(device=local_rank, max_points=n, max_w=W, max_h=H, max_batch=B)
+    cams_all, cfg = cameras_for(spec, rank * 1000, ring)
+    style = cfg.style(color_mode=spec["color_mode"])
+    rgba = torch.empty((B, H, W, 4), dtype=torch.uint8, device="cuda")
+    host_rgba = torch.empty((B, H, W, 4), dtype=torch.uint8).pin_memory()
+    slots = ring // B
+
+    def step_device(s):
+        k = (s % slots) * B
+        ctx.render_frames(resident[k:k + B], cams_all[k:k + B], style, radius=radius, out_rgba=rgba)
+
+    def step_host(s):
+        k = (s % slots) * B
+        ctx.render_frames_host(host[k:k + B], cams_all[k:k + B], style, radius_host=radius_np, out_rgba=host_rgba)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+
+    # ---------------- device-resident throughput ----------------
+    for s in range(args.warmup):
+        step_device(s)
+    barrier()
+    ctx.profile_read()
+    if not args.no_profile:
+        ctx.profile(True)
+    launches0 = ctx.counters()["launches"]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.begin()
+    barrier()
+    ev0.record()
+    for s in range(args.steps):
+        step_device(args.warmup + s)
+    ev1.record()
+    barrier()
+    if sampler:
+        sampler.end()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    ctx.profile(False)
+    prof = ctx.profile_read()
+    counters = ctx.counters()
+    launches = counters["launches"] - launches0
+    frames_total = world * B * args.steps
+    fps = frames_total / (dev_ms * 1e-3)
+
+    # ---------------- end to end through the host-buffer entry ----------------
+    e2e = None
+    if not args.no_e2e:
+        for s in range(max(args.warmup, 1)):
+            step_host(s)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            step_host(args.warmup + s)
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": frames_total / e2e_s, "unit": "frames/s",
+               "h2d_bytes_per_step": int(B * spec["input_bytes_per_frame"] + (n * 4 if spec["radii"] else 0)),
+               "d2h_bytes_per_step": int(B * W * H * 4), "ms_per_step": e2e_s / args.steps * 1e3,
+               "api": "pcr_render_frames_host (pinned host trajectory in, pinned host RGBA8 out; copies overlap kernels)"}
+    if sampler:
+        sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    roofline = None
+    kernels = {}
+    if prof:
+        total_ms = sum(v[0] for v in prof.values())
+        for name, (ms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+            kernels[name] = {"ms_total": round(ms, 4), "launches": int(cnt), "us_per_launch": round(ms / cnt * 1e3, 3),
+                             "share": round(ms / total_ms, 4)}
+        top = max(prof.items(), key=lambda kv: kv[1][0])
+        top_ms, top_cnt = top[1]
+        frames_per_launch = B * args.steps / top_cnt
+        bytes_per_launch = spec["algorithmic_bytes_per_frame"] * frames_per_launch
+        achieved = bytes_per_launch / (top_ms / top_cnt * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.isfile(tpath):
+            traffic = json.load(open(tpath)).get(args.workload, {}).get(top[0])
+        roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": bytes_per_launch, "frames_per_launch": frames_per_launch,
+                    "us_per_launch": top_ms / top_cnt * 1e3,
+                    "whole_step_achieved_gbs": spec["algorithmic_bytes_per_frame"] * B * args.steps / (dev_ms * 1e-3) / 1e9,
+                    "note": "algorithmic bytes = N*b_in + W*H*(8+4) per frame (SURVEY.md 8d); the path is bound by sphere-pixel "
+                            "tests, not by HBM bytes"}
+
+    line = {"metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "mpoints_per_s": fps * n / 1e6,
+            "config": config_dict(args.workload, spec, ring, world),
+            "e2e": e2e, "gpu_launches": int(launches), "kernels": kernels, "roofline": roofline,
+            "clocks": sampler.summary() if sampler else None,
+            "pairs_last_frame": counters["pairs_last_frame"], "overflow_frames": counters["overflow_frames"]}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(spec, host_np, radius_np)
+    print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -144,6 +144,12 @@ int pcr_standardize(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, in
                     float* d_pos_out, float* d_attr_out, float* d_vel_out, double* d_stats,
                     void* stream);
 
+/* transform_coordinates alone (traj_ball_renderer.py:204-221; no-flip: traj_b0.py:62-82,
+ * traj_original.py:40-60) on an already standardised (n, cols) float32 array:
+ * pos' = (-+z, x, y + z_lift), vel' = (-+vz, vx, vy).  d_out must not alias d_in. */
+int pcr_transform_coordinates(pcr_ctx* ctx, const float* d_in, int64_t n, int cols, int flip_x,
+                              float z_lift, float* d_out, void* stream);
+
 /* K2+K3(+K4) — render already-transformed spheres (what generate_xml_content would emit).
  *   d_pos    [n] float4 (x,y,z,r) world space ; d_attr [n] float4 (r,g,b,_)
  *   id_base  added to the local index to form the stored point id (point sharding)
@@ -206,6 +212,14 @@ int pcr_standardize_with_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, in
  * out[0] = kernels launched, out[1] = (tile,sphere) pairs of the last frame,
  * out[2] = frames that overflowed pair_capacity, out[3] = spheres culled (last frame). */
 int pcr_counters(pcr_ctx* ctx, int64_t out[4], void* stream);
+
+/* Per-kernel timing.  While enabled, every kernel launch is bracketed by two CUDA events on the
+ * launching stream.  pcr_profile_read waits for the recorded events, writes the summed
+ * milliseconds and launch counts per kernel id (index k <-> pcr_kernel_name(k)), clears the
+ * records and returns the number of kernel ids (<= capacity), or a negative status. */
+int pcr_profile(pcr_ctx* ctx, int enable);
+int pcr_profile_read(pcr_ctx* ctx, double* ms_out, int64_t* count_out, int capacity);
+const char* pcr_kernel_name(int kernel_id);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,119 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (stub-imported from
+/root/reference, oracle/ref_import.py) on seeded synthetic inputs — TEST INFRASTRUCTURE.
+
+Run here (the reference cannot travel to the GPU box):  python -m oracle.gen_golden
+What gets pinned:
+  standardize.npz   standardize_point_cloud / transform_coordinates outputs of every flavour
+  camera.npz        compute_camera_position of every script at characteristic frames
+  scene_*.npz       the scene generate_xml_content emits (centres, radius, reflectance, sensor,
+                    floor, emitter), parsed back by oracle/scene_from_xml.py
+  vis_example.npz   visibility ids of the C oracle for the example scene at 200x150 and the
+                    sha256 of the full C1 (800x600) key buffer — NOT pinned by the reference
+                    (Mitsuba absent): guards the oracle against silent change only.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import pcr_oracle as orc  # noqa: E402
+from oracle import ref_import, scene_from_xml  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+CAMERA_FRAMES = np.array([0, 1, 19, 20, 57, 100, 198, 199, 200, 205, 210, 219])
+
+
+def synth(n, cols, seed, dtype):
+    rng = np.random.default_rng(seed)
+    a = rng.standard_normal((n, cols)) * np.array([1.0, 0.6, 1.7, 3, 3, 3][:cols]) + np.array([0.3, -2.0, 5.0, 0, 0, 0][:cols])
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_import.load()
+    ex, ball, orig, b0, b1, traj, vel = (ref[k] for k in ("example_renderer", "traj_ball_renderer", "traj_original",
+                                                           "traj_b0", "traj_b1", "traj_renderer", "traj_vel_renderer"))
+
+    # ---- a1 / a2 -----------------------------------------------------------------------------
+    g = {}
+    for tag, n, cols, dtype in (("f32_3", 257, 3, np.float32), ("f64_3", 257, 3, np.float64),
+                                ("f32_6", 193, 6, np.float32), ("f64_6", 193, 6, np.float64)):
+        x = synth(n, cols, 11 + cols, dtype)
+        g[f"in_{tag}"] = x
+        if cols == 3:
+            s = ex.PointCloudRenderer.standardize_point_cloud(x.copy())
+            g[f"std_example_{tag}"] = s
+            p = s[:, [2, 0, 1]]
+            p[:, 0] *= -1
+            p[:, 2] += 0.0125                                     # example_renderer.py:171-173
+            g[f"xf_example_{tag}"] = p
+        for name, cls in (("ball", ball.TrajectoryBallRenderer), ("traj", traj.TrajectoryRenderer),
+                          ("vel", vel.TrajectoryVelRenderer), ("orig", orig.FixedFrame199Renderer),
+                          ("b0", b0.FixedFrame199Renderer), ("b1", b1.FixedFrame199Renderer)):
+            s = cls.standardize_point_cloud(x.copy())
+            g[f"std_{name}_{tag}"] = s
+            g[f"xf_{name}_{tag}"] = cls.transform_coordinates(s.copy())
+    np.savez_compressed(os.path.join(OUT, "standardize.npz"), **g)
+
+    # ---- a4 ----------------------------------------------------------------------------------
+    cams = {"frames": CAMERA_FRAMES}
+    for name, cls in (("traj_ball", ball.TrajectoryBallRenderer), ("traj_vel", vel.TrajectoryVelRenderer),
+                      ("traj_original", orig.FixedFrame199Renderer), ("traj_b0", b0.FixedFrame199Renderer),
+                      ("traj_b1", b1.FixedFrame199Renderer)):
+        cams[name] = np.array([cls.compute_camera_position(int(f), 220) for f in CAMERA_FRAMES], np.float64)
+    cams["traj"] = np.array([traj.TrajectoryRenderer.compute_camera_position(int(f), 220) for f in CAMERA_FRAMES], np.float64)
+    np.savez_compressed(os.path.join(OUT, "camera.npz"), **cams)
+
+    # ---- a6: emitted scenes -----------------------------------------------------------------
+    def dump(name, xml, pcl_in, frame):
+        sc = scene_from_xml.parse_scene(xml)
+        np.savez_compressed(os.path.join(OUT, f"scene_{name}.npz"), input=pcl_in, frame=frame,
+                            centers=sc["centers"], radius=sc["radius"], reflectance=sc["reflectance"],
+                            origin=np.array(sc["origin"]), target=np.array(sc["target"]), up=np.array(sc["up"]),
+                            fov=sc["fov"], near_clip=sc["near_clip"], far_clip=sc["far_clip"],
+                            width=sc["width"], height=sc["height"], spp=sc["spp"],
+                            floor_z=sc["floor_z"], floor_min=np.array(sc["floor_min"]), floor_max=np.array(sc["floor_max"]),
+                            light_z=sc["light_z"], light_half=sc["light_half"], radiance=sc["radiance"])
+        return sc
+
+    rng = np.random.default_rng(0)
+    c1 = rng.standard_normal((2048, 3)).astype(np.float32)                       # config C1's cloud
+    r = ex.PointCloudRenderer("c1.npy")
+    p = r.standardize_point_cloud(c1.copy())
+    p = p[:, [2, 0, 1]]
+    p[:, 0] *= -1
+    p[:, 2] += 0.0125
+    sc_ex = dump("example", r.generate_xml_content(p), c1, 0)
+
+    x3 = synth(160, 3, 5, np.float32)       # position-only input: no trail files are written
+    for name, cls, frame in (("traj_ball", ball.TrajectoryBallRenderer, 57), ("traj_original", orig.FixedFrame199Renderer, 199),
+                             ("traj_b0", b0.FixedFrame199Renderer, 205), ("traj_b1", b1.FixedFrame199Renderer, 100)):
+        rr = cls("f.npy")
+        q = rr.transform_coordinates(rr.standardize_point_cloud(x3.copy()))
+        dump(name, rr.generate_xml_content(q, frame_index=frame, total_frames=220), x3, frame)
+
+    # ---- oracle self-pin (unpinned by the reference) -----------------------------------------
+    pos4 = np.concatenate([sc_ex["centers"], sc_ex["radius"][:, None]], axis=1).astype(np.float32)
+    scene = orc.make_scene(True, sc_ex["floor_z"], sc_ex["floor_min"], sc_ex["floor_max"], 1.0, sc_ex["light_z"],
+                           sc_ex["light_half"], sc_ex["radiance"], 1.0)
+    small = orc.camera_frame(sc_ex["origin"], sc_ex["target"], sc_ex["up"], sc_ex["fov"], sc_ex["near_clip"],
+                             sc_ex["far_clip"], 200, 150)
+    vis_small = orc.visibility(pos4, small, scene, brute_force=True)
+    full = orc.camera_frame(sc_ex["origin"], sc_ex["target"], sc_ex["up"], sc_ex["fov"], sc_ex["near_clip"],
+                            sc_ex["far_clip"], 800, 600)
+    vis_full = orc.visibility(pos4, full, scene)
+    attr4 = np.concatenate([sc_ex["reflectance"], np.zeros((len(pos4), 1), np.float32)], axis=1)
+    img_small = orc.shade(vis_small, pos4, attr4, small, scene)
+    np.savez_compressed(os.path.join(OUT, "vis_example.npz"), keys_200x150=vis_small, rgba_200x150=img_small,
+                        sha256_800x600=hashlib.sha256(vis_full.tobytes()).hexdigest())
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -133,6 +133,10 @@ static inline uint64_t floor_key(const orc_frame* f, const orc_scene* s, float u
 static int sphere_bbox(const orc_frame* f, const float* c, float r, int* i0, int* i1, int* j0, int* j1)
 {
     const int W = f->W, H = f->H;
+    /* a non-finite centre or radius can never pass the ray test (disc is NaN or -inf, or the
+     * depth is -inf); r enters the test only as r*r */
+    if (!(isfinite(c[0]) && isfinite(c[1]) && isfinite(c[2]) && isfinite(r))) return 0;
+    r = fabsf(r);
     if (c[2] + r < f->near_clip) return 0;
     if (c[2] - r <= 1e-6f) { *i0 = 0; *i1 = W - 1; *j0 = 0; *j1 = H - 1; return 1; }
     double cz = c[2], rr = (double)r * 1.0001 + 1e-7;

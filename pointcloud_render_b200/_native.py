@@ -22,6 +22,7 @@ SYMBOLS = (
     "pcr_abi_version", "pcr_create", "pcr_destroy", "pcr_last_error", "pcr_camera_frame",
     "pcr_standardize", "pcr_render", "pcr_shade", "pcr_render_frames", "pcr_render_frames_host",
     "pcr_zmin", "pcr_zmerge_nccl", "pcr_stats_partial", "pcr_standardize_with_stats", "pcr_counters",
+    "pcr_transform_coordinates", "pcr_profile", "pcr_profile_read", "pcr_kernel_name",
 )
 
 
@@ -81,9 +82,14 @@ def load_library():
     L.pcr_stats_partial.argtypes = [vp, vp, i32, i64, i32, vp, vp]
     L.pcr_standardize_with_stats.argtypes = [vp, vp, i32, i64, i32, vp, vp, styp, vp, vp, vp, vp, vp]
     L.pcr_counters.argtypes = [vp, ctypes.POINTER(i64), vp]
+    L.pcr_transform_coordinates.argtypes = [vp, vp, i64, i32, i32, ctypes.c_float, vp, vp]
+    L.pcr_profile.argtypes = [vp, i32]
+    L.pcr_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), i32]
+    L.pcr_kernel_name.argtypes = [i32]
+    L.pcr_kernel_name.restype = ctypes.c_char_p
     for name in SYMBOLS:
         fn = getattr(L, name)
-        if name not in ("pcr_destroy", "pcr_last_error"):
+        if name not in ("pcr_destroy", "pcr_last_error", "pcr_kernel_name"):
             fn.restype = i32
     _lib = L
     return L
@@ -189,6 +195,16 @@ class Context:
             out.append(stats)
         return tuple(out)
 
+    def transform_coordinates(self, pcl, flip_x=True, z_lift=0.0125, stream=None):
+        """(N,3|6) float32 CUDA tensor -> transformed copy (transform_coordinates alone)."""
+        import torch
+        assert pcl.is_cuda and pcl.is_contiguous() and pcl.dtype == torch.float32
+        n, cols = pcl.shape
+        out = torch.empty_like(pcl)
+        self._check(self.lib.pcr_transform_coordinates(self.handle, _ptr(pcl), n, cols, int(bool(flip_x)), float(z_lift),
+                                                       _ptr(out), _stream_ptr(stream)))
+        return out
+
     def stats_partial(self, pts, stream=None):
         import torch
         n, cols = pts.shape
@@ -265,6 +281,18 @@ class Context:
     def zmin_(self, dst, src, stream=None):
         self._check(self.lib.pcr_zmin(self.handle, _ptr(dst), _ptr(src), dst.numel(), _stream_ptr(stream)))
         return dst
+
+    def profile(self, enable=True):
+        self._check(self.lib.pcr_profile(self.handle, int(bool(enable))))
+
+    def profile_read(self):
+        """{kernel name: (total ms, launches)} since the last read (waits for the recorded events)."""
+        ms = (ctypes.c_double * 32)()
+        cnt = (ctypes.c_int64 * 32)()
+        k = self.lib.pcr_profile_read(self.handle, ms, cnt, 32)
+        if k < 0:
+            self._check(k)
+        return {self.lib.pcr_kernel_name(i).decode(): (ms[i], cnt[i]) for i in range(k) if cnt[i] > 0}
 
     def counters(self, stream=None):
         out = (ctypes.c_int64 * 4)()

@@ -22,6 +22,14 @@ namespace {
 constexpr int RING_SLOTS = 4;
 constexpr int MAX_STAT_BLOCKS = 1184;   // 148 SMs x 8
 
+enum KernelId { KID_STATS = 0, KID_TRANSFORM, KID_PROJECT, KID_SCAN, KID_SCATTER, KID_RASTER, KID_RASTER_NAIVE, KID_SHADE,
+                KID_ZMIN, KID_AXIS, KID_COUNT };
+const char* const kKernelNames[KID_COUNT] = {"k_stats", "k_transform", "k_project_count", "k_scan_tiles", "k_scatter",
+                                             "k_raster_tiles", "k_raster_naive", "k_shade", "k_zmin", "k_axis_transform"};
+constexpr size_t PROF_MAX_RECORDS = 1 << 16;
+
+struct ProfRec { int kid; cudaEvent_t a, b; };
+
 }  // namespace
 
 struct pcr_ctx {
@@ -58,6 +66,11 @@ struct pcr_ctx {
     float *stage_radius = nullptr, *stage_rgb = nullptr;
 
     long long last_overflow_frames = 0;
+
+    // per-kernel CUDA-event timing (pcr_profile / pcr_profile_read)
+    bool profiling = false;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> prof_pool;
 };
 
 namespace {
@@ -77,11 +90,39 @@ int fail(pcr_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess)
         if (e_ != cudaSuccess) return fail(ctx, PCR_ERR_CUDA, #call, e_);   \
     } while (0)
 
-#define CKL(name)                                                           \
-    do {                                                                    \
-        cudaError_t e_ = cudaGetLastError();                                \
-        if (e_ != cudaSuccess) return fail(ctx, PCR_ERR_CUDA, name, e_);    \
-        ctx->launches++;                                                    \
+cudaEvent_t prof_event(pcr_ctx* c)
+{
+    cudaEvent_t e = nullptr;
+    if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+    if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return e;
+}
+
+inline void prof_begin(pcr_ctx* c, int kid, cudaStream_t s)
+{
+    if (!c->profiling || c->prof.size() >= PROF_MAX_RECORDS) return;
+    ProfRec r{kid, prof_event(c), prof_event(c)};
+    if (!r.a || !r.b) return;
+    cudaEventRecord(r.a, s);
+    c->prof.push_back(r);
+}
+
+inline void prof_end(pcr_ctx* c, int kid, cudaStream_t s)
+{
+    if (!c->profiling || c->prof.empty() || c->prof.back().kid != kid) return;
+    cudaEventRecord(c->prof.back().b, s);
+}
+
+// LAUNCH(kernel id, stream, kernel<<<...>>>(...)) — counts the launch and, when profiling is on,
+// brackets it with two events on the launching stream.
+#define LAUNCH(kid, stream, ...)                                                        \
+    do {                                                                                \
+        prof_begin(ctx, kid, stream);                                                   \
+        __VA_ARGS__;                                                                    \
+        cudaError_t e_ = cudaGetLastError();                                            \
+        prof_end(ctx, kid, stream);                                                     \
+        if (e_ != cudaSuccess) return fail(ctx, PCR_ERR_CUDA, kKernelNames[kid], e_);   \
+        ctx->launches++;                                                                \
     } while (0)
 
 StyleDev to_style_dev(const pcr_style* s)
@@ -169,10 +210,9 @@ int launch_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, long long n, int
     blocks = std::max(blocks, 1);
     dim3 grid(blocks, nb);
     if (in_is_f64)
-        k_stats<double><<<grid, 256, 0, stream>>>((const double*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, ctx->done, finalize);
+        LAUNCH(KID_STATS, stream, k_stats<double><<<grid, 256, 0, stream>>>((const double*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, ctx->done, finalize));
     else
-        k_stats<float><<<grid, 256, 0, stream>>>((const float*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, ctx->done, finalize);
-    CKL("k_stats");
+        LAUNCH(KID_STATS, stream, k_stats<float><<<grid, 256, 0, stream>>>((const float*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, ctx->done, finalize));
     return PCR_OK;
 }
 
@@ -182,10 +222,9 @@ int launch_transform(pcr_ctx* ctx, const void* d_in, int in_is_f64, long long n,
 {
     dim3 grid((unsigned)((n + 255) / 256), nb);
     if (in_is_f64)
-        k_transform<double><<<grid, 256, 0, stream>>>((const double*)d_in, n, cols, frame_stride, d_radius, d_rgb, stats, st, pos, attr, vel, out_stride);
+        LAUNCH(KID_TRANSFORM, stream, k_transform<double><<<grid, 256, 0, stream>>>((const double*)d_in, n, cols, frame_stride, d_radius, d_rgb, stats, st, pos, attr, vel, out_stride));
     else
-        k_transform<float><<<grid, 256, 0, stream>>>((const float*)d_in, n, cols, frame_stride, d_radius, d_rgb, stats, st, pos, attr, vel, out_stride);
-    CKL("k_transform");
+        LAUNCH(KID_TRANSFORM, stream, k_transform<float><<<grid, 256, 0, stream>>>((const float*)d_in, n, cols, frame_stride, d_radius, d_rgb, stats, st, pos, attr, vel, out_stride));
     return PCR_OK;
 }
 
@@ -198,32 +237,26 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
     const int tiles = ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
     if (n > 0) {
         dim3 grid((unsigned)((n + 255) / 256), nb);
-        k_project_count<<<grid, 256, 0, stream>>>(pos, n, in_stride, ctx->d_frames, ctx->sph, ctx->rect, ctx->max_points, bin);
-        CKL("k_project_count");
+        LAUNCH(KID_PROJECT, stream, k_project_count<<<grid, 256, 0, stream>>>(pos, n, in_stride, ctx->d_frames, ctx->sph, ctx->rect, ctx->max_points, bin));
     }
-    k_scan_tiles<<<nb, 1024, 0, stream>>>(ctx->d_frames, bin);
-    CKL("k_scan_tiles");
+    LAUNCH(KID_SCAN, stream, k_scan_tiles<<<nb, 1024, 0, stream>>>(ctx->d_frames, bin));
     if (n > 0) {
         dim3 grid((unsigned)((n + 255) / 256), nb);
-        k_scatter<<<grid, 256, 0, stream>>>(n, ctx->d_frames, ctx->rect, ctx->max_points, bin);
-        CKL("k_scatter");
+        LAUNCH(KID_SCATTER, stream, k_scatter<<<grid, 256, 0, stream>>>(n, ctx->d_frames, ctx->rect, ctx->max_points, bin));
     }
     {
         dim3 grid(tiles, nb);
-        k_raster_tiles<<<grid, RASTER_THREADS, 0, stream>>>(ctx->d_frames, st, ctx->sph, ctx->rect, ctx->max_points, bin, id_base, vis, vis_stride);
-        CKL("k_raster_tiles");
+        LAUNCH(KID_RASTER, stream, k_raster_tiles<<<grid, RASTER_THREADS, 0, stream>>>(ctx->d_frames, st, ctx->sph, ctx->rect, ctx->max_points, bin, id_base, vis, vis_stride));
     }
     if (n > 0) {
         dim3 grid(ctx->num_sms * 4, nb);
-        k_raster_naive<<<grid, 256, 0, stream>>>(n, ctx->d_frames, ctx->sph, ctx->rect, ctx->max_points, bin, id_base,
-                                                 (unsigned long long*)vis, vis_stride);
-        CKL("k_raster_naive");
+        LAUNCH(KID_RASTER_NAIVE, stream, k_raster_naive<<<grid, 256, 0, stream>>>(n, ctx->d_frames, ctx->sph, ctx->rect, ctx->max_points, bin, id_base,
+                                                                                  (unsigned long long*)vis, vis_stride));
     }
     if (rgba) {
         dim3 grid((unsigned)(((long long)W * H + 255) / 256), nb);
-        k_shade<<<grid, 256, 0, stream>>>(ctx->d_frames, st, vis, vis_stride, pos, attr, in_stride, n, id_base, owner_only,
-                                          (uint32_t*)rgba, rgba_stride);
-        CKL("k_shade");
+        LAUNCH(KID_SHADE, stream, k_shade<<<grid, 256, 0, stream>>>(ctx->d_frames, st, vis, vis_stride, pos, attr, in_stride, n, id_base, owner_only,
+                                                                    (uint32_t*)rgba, rgba_stride));
     }
     return PCR_OK;
 }
@@ -320,6 +353,8 @@ void pcr_destroy(pcr_ctx* ctx)
         if (ctx->ev_comp[k]) cudaEventDestroy(ctx->ev_comp[k]);
         if (ctx->ev_d2h[k]) cudaEventDestroy(ctx->ev_d2h[k]);
     }
+    for (ProfRec& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
@@ -369,6 +404,19 @@ int pcr_standardize(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, in
     return PCR_OK;
 }
 
+int pcr_transform_coordinates(pcr_ctx* ctx, const float* d_in, int64_t n, int cols, int flip_x, float z_lift, float* d_out,
+                              void* stream)
+{
+    if (!ctx) return PCR_ERR_INVALID;
+    if (n < 0 || (cols != 3 && cols != 6)) return fail(ctx, PCR_ERR_INVALID, "n < 0 or cols not 3|6");
+    if (n == 0) return PCR_OK;
+    if (!d_in || !d_out || d_in == d_out) return fail(ctx, PCR_ERR_INVALID, "pcr_transform_coordinates: NULL or aliased buffer");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    LAUNCH(KID_AXIS, s, k_axis_transform<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_in, n, cols, flip_x, z_lift, d_out));
+    return PCR_OK;
+}
+
 int pcr_render(pcr_ctx* ctx, const float* d_pos, const float* d_attr, int64_t n, uint32_t id_base, const pcr_camera* cam,
                const pcr_style* style, uint64_t* d_vis, uint8_t* d_rgba, void* stream)
 {
@@ -397,9 +445,8 @@ int pcr_shade(pcr_ctx* ctx, const uint64_t* d_vis, const float* d_pos, const flo
     if (rc) return rc;
     const long long px = (long long)cam->width * cam->height;
     dim3 grid((unsigned)((px + 255) / 256), 1);
-    k_shade<<<grid, 256, 0, s>>>(ctx->d_frames, to_style_dev(style), d_vis, px, (const float4*)d_pos, (const float4*)d_attr, 0, n,
-                                 id_base, owner_only, (uint32_t*)d_rgba, px);
-    CKL("k_shade");
+    LAUNCH(KID_SHADE, s, k_shade<<<grid, 256, 0, s>>>(ctx->d_frames, to_style_dev(style), d_vis, px, (const float4*)d_pos, (const float4*)d_attr, 0, n,
+                                                      id_base, owner_only, (uint32_t*)d_rgba, px));
     return PCR_OK;
 }
 
@@ -510,8 +557,8 @@ int pcr_zmin(pcr_ctx* ctx, uint64_t* d_dst, const uint64_t* d_src, int64_t n_px,
     if (n_px == 0) return PCR_OK;
     CK(cudaSetDevice(ctx->device));
     int blocks = (int)std::min<long long>((n_px + 255) / 256, (long long)ctx->num_sms * 16);
-    k_zmin<<<blocks, 256, 0, (cudaStream_t)stream>>>((unsigned long long*)d_dst, (const unsigned long long*)d_src, n_px);
-    CKL("k_zmin");
+    cudaStream_t s = (cudaStream_t)stream;
+    LAUNCH(KID_ZMIN, s, k_zmin<<<blocks, 256, 0, s>>>((unsigned long long*)d_dst, (const unsigned long long*)d_src, n_px));
     return PCR_OK;
 }
 
@@ -550,5 +597,34 @@ int pcr_counters(pcr_ctx* ctx, int64_t out[4], void* stream)
     out[0] = ctx->launches; out[1] = (int64_t)pairs; out[2] = nov; out[3] = 0;
     return PCR_OK;
 }
+
+int pcr_profile(pcr_ctx* ctx, int enable)
+{
+    if (!ctx) return PCR_ERR_INVALID;
+    ctx->profiling = enable != 0;
+    return PCR_OK;
+}
+
+int pcr_profile_read(pcr_ctx* ctx, double* ms_out, int64_t* count_out, int capacity)
+{
+    if (!ctx || !ms_out || !count_out || capacity < KID_COUNT) return ctx ? fail(ctx, PCR_ERR_INVALID, "pcr_profile_read: buffers too small") : PCR_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    for (int k = 0; k < capacity; ++k) { ms_out[k] = 0.0; count_out[k] = 0; }
+    for (ProfRec& r : ctx->prof) {
+        float ms = 0.0f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            ms_out[r.kid] += (double)ms;
+            count_out[r.kid] += 1;
+        } else {
+            cudaGetLastError();
+        }
+        ctx->prof_pool.push_back(r.a);
+        ctx->prof_pool.push_back(r.b);
+    }
+    ctx->prof.clear();
+    return KID_COUNT;
+}
+
+const char* pcr_kernel_name(int kernel_id) { return kernel_id >= 0 && kernel_id < KID_COUNT ? kKernelNames[kernel_id] : ""; }
 
 }  // extern "C"

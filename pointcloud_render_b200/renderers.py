@@ -1,0 +1,312 @@
+"""Host-side mirror of the reference's renderer classes, backed by the pcr C ABI.
+
+Same class and method names, argument meaning and error behaviour as the reference scripts:
+
+  PointCloudRenderer        example_renderer.py:77-199
+  TrajectoryBallRenderer    traj_ball_renderer.py:80-416
+  FixedFrame199Renderer     traj_original.py:6-142   (no x flip, fixed camera)
+  TrajB0Renderer            traj_b0.py:6-191         (class is also called FixedFrame199Renderer there)
+  TrajB1Renderer            traj_b1.py:6-191
+  TrajectoryRenderer        traj_renderer.py:87-676  (points drawn as spheres — droplet mesh and
+  TrajectoryVelRenderer     traj_vel_renderer.py:80-530  trails are SURVEY.md §8f "next" rows)
+
+What changes is the seam: `render_scene` takes the transformed point array
+instead of an XML path, and nothing is written to disk between the stages — centres, radii and
+colours stay in HBM from K1 to K4.  There is no CPU fallback: every array method runs through
+libpcr.so on a CUDA device and raises if either is missing.
+"""
+import os
+
+import numpy as np
+
+from . import _native
+from .io import load_point_cloud as _load_point_cloud, write_png
+from .presets import PRESETS
+
+_ENGINES = {}
+
+
+def _engine(device, n, w, h, batch=1):
+    """One grow-only pcr context per device (scratch for n points, w x h pixels)."""
+    key = int(device)
+    eng = _ENGINES.get(key)
+    if eng is None or eng.max_points < n or eng.max_w < w or eng.max_h < h or eng.max_batch < batch:
+        if eng is not None:
+            n, w, h, batch = max(n, eng.max_points), max(w, eng.max_w), max(h, eng.max_h), max(batch, eng.max_batch)
+            eng.close()
+        eng = _native.Context(device=key, max_points=max(int(n), 1), max_w=int(w), max_h=int(h), max_batch=int(batch))
+        _ENGINES[key] = eng
+    return eng
+
+
+def release_engines():
+    for eng in _ENGINES.values():
+        eng.close()
+    _ENGINES.clear()
+
+
+def _to_device(pcl, device):
+    """numpy / torch (any device) -> contiguous CUDA tensor f32|f64, plus 'was numpy' flag."""
+    import torch
+    if isinstance(pcl, torch.Tensor):
+        t, was_np = pcl, False
+    else:
+        a = np.asarray(pcl)
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float64)          # numpy promotes ints to f64 in mean/divide too
+        t, was_np = torch.from_numpy(np.ascontiguousarray(a)), True
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float64)
+    return t.to(f"cuda:{device}", non_blocking=True).contiguous(), was_np
+
+
+def _back(t, was_np):
+    return t.cpu().numpy() if was_np else t
+
+
+class RenderedScene:
+    """What render_scene returns (stands in for the Mitsuba image tensor): sRGB8 image and the
+    visibility keys, both still on the device."""
+
+    def __init__(self, rgba, vis):
+        self.rgba = rgba      # (H,W,4) uint8 CUDA tensor
+        self.vis = vis        # (H,W) int64 CUDA tensor holding the uint64 keys
+
+    def numpy(self):
+        return self.rgba.cpu().numpy()
+
+    def point_ids(self):
+        return _native.keys_to_ids(self.vis)
+
+
+class PointCloudRenderer:
+    """example_renderer.py:77 — one cloud -> one image, fixed camera."""
+    PRESET = "example"
+    DEVICE = 0
+    WITH_VELOCITY = False            # load_point_cloud reads x,y,z only (example_renderer.py:108-109)
+
+    def __init__(self, file_path, output_folder=None, width=None, height=None, color_mode=_native.COLOR_CONST,
+                 radius=None, user_rgb=None):
+        self.file_path = file_path
+        self.folder, full_filename = os.path.split(file_path) if file_path else ("", "")
+        self.folder = self.folder or '.'
+        self.filename, _ = os.path.splitext(full_filename)
+        self.output_folder = output_folder
+        self.config = PRESETS[self.PRESET]
+        self.width = int(width or self.config.width)
+        self.height = int(height or self.config.height)
+        self.color_mode = int(color_mode)
+        self.radius = radius          # None -> the BALL_SEGMENT literal; float; or per-point array (extension)
+        self.user_rgb = user_rgb
+
+    # ---- hooks the reference exposes ----------------------------------------------------
+    @staticmethod
+    def compute_color(x=0.0, y=0.0, z=0.0, noise_seed=0):
+        """example_renderer.py:89-92: constant grey, arguments ignored (colour modes 1-3 of
+        pcr_style are the extensions north_star names; mode 0 is this)."""
+        g = 0.3
+        return np.array([g, g, g])
+
+    @classmethod
+    def standardize_point_cloud(cls, pcl):
+        """example_renderer.py:94-98 / traj_ball_renderer.py:190-202 on the device (K0 + K1 with
+        the axis transform switched off).  numpy in -> numpy out, CUDA tensor in -> CUDA tensor out."""
+        import torch
+        t, was_np = _to_device(pcl, cls.DEVICE)
+        if t.dim() != 2 or t.shape[1] not in (3, 6):
+            raise ValueError("point cloud must be (N,3) or (N,6)")
+        n, cols = t.shape
+        eng = _engine(cls.DEVICE, n, 16, 16)
+        style = PRESETS[cls.PRESET].style(xform=1)
+        if cols == 6:
+            pos, _, vel = eng.standardize(t, style, want_vel=True)
+            out = torch.cat([pos[:, :3], vel[:, :3]], dim=1).contiguous()
+        else:
+            pos, _ = eng.standardize(t, style)
+            out = pos[:, :3].contiguous()
+        return _back(out, was_np)
+
+    @classmethod
+    def transform_coordinates(cls, pcl):
+        """traj_ball_renderer.py:204-221 (and the inline example_renderer.py:171-173)."""
+        import torch
+        t, was_np = _to_device(pcl, cls.DEVICE)
+        t = t.to(torch.float32)
+        cfg = PRESETS[cls.PRESET]
+        eng = _engine(cls.DEVICE, t.shape[0], 16, 16)
+        return _back(eng.transform_coordinates(t, flip_x=cfg.flip_x, z_lift=cfg.z_lift), was_np)
+
+    @classmethod
+    def compute_camera_position(cls, frame_index=0, total_frames=220):
+        return PRESETS[cls.PRESET].camera_position(frame_index, total_frames)
+
+    def load_point_cloud(self):
+        return _load_point_cloud(self.file_path, with_velocity=self.WITH_VELOCITY)
+
+    @classmethod
+    def init_mitsuba_variant(cls):
+        """Name kept from example_renderer.py:137-151.  There is no variant chain any more: the
+        only back end is the sm_100a extension, so this loads it and fails loudly otherwise."""
+        import torch
+        _native.load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("pcr needs a CUDA device (no CPU fallback)")
+        print(f'Using CUDA GPU (pcr / {torch.cuda.get_device_name(cls.DEVICE)})')
+        return True
+
+    init_device = init_mitsuba_variant
+
+    # ---- the seam: render_scene / save_scene ---------------------------------------------
+    def _style(self):
+        return self.config.style(color_mode=self.color_mode)
+
+    def _per_point(self, n, device):
+        import torch
+        radius = rgb = None
+        if self.radius is not None and np.ndim(self.radius) > 0:
+            radius = torch.as_tensor(np.asarray(self.radius, np.float32)).to(device)
+            if radius.numel() != n:
+                raise ValueError("per-point radius must have one entry per point")
+        if self.user_rgb is not None:
+            rgb = torch.as_tensor(np.asarray(self.user_rgb, np.float32)).to(device).contiguous()
+            if rgb.numel() != 3 * n:
+                raise ValueError("user_rgb must be (N,3)")
+        return radius, rgb
+
+    def render_scene(self, pcl, frame_index=0, total_frames=220):
+        """Replaces generate_xml_content + save_xml + mi.load_file + mi.render
+        (example_renderer.py:113-157): `pcl` is the standardised, transformed (N,3|6) array."""
+        import torch
+        t, _ = _to_device(pcl, self.DEVICE)
+        t = t.to(torch.float32)
+        n = t.shape[0]
+        eng = _engine(self.DEVICE, n, self.width, self.height)
+        style = self._style()
+        if self.radius is not None and np.ndim(self.radius) == 0:
+            style.radius = float(self.radius)
+        radius, rgb = self._per_point(n, t.device)
+        # colour hook + float4 packing without touching the coordinates again (xform = 1 keeps
+        # positions as they are; centre 0 / scale 1 are injected so nothing is re-standardised)
+        stats = torch.zeros(10, dtype=torch.float64, device=t.device)
+        stats[9] = 1.0
+        if n > 0:
+            stats[3:9] = eng.stats_partial(t)[3:9]      # min / max of the cloud for the position colormap
+        st1 = self.config.style(color_mode=self.color_mode, xform=1)
+        st1.radius = style.radius
+        pos4, attr4 = eng.standardize_with_stats(t, st1, stats, radius=radius, rgb=rgb)
+        cam = self.config.camera(frame_index, total_frames, self.width, self.height)
+        vis, rgba = eng.render(pos4, attr4, cam, style)
+        return RenderedScene(rgba, vis)
+
+    @staticmethod
+    def save_scene(output_file_path, rendered_scene):
+        """example_renderer.py:159-161: the sRGB transfer already happened in K4; this is the PNG."""
+        write_png(f'{output_file_path}.png', rendered_scene.numpy())
+
+    def _output_path(self, output_filename):
+        if self.output_folder:
+            os.makedirs(self.output_folder, exist_ok=True)
+            return os.path.join(self.output_folder, output_filename)
+        return os.path.join(self.folder, output_filename)
+
+    def process(self):
+        """example_renderer.py:163-199.  A 3-D input renders every frame to the same file name
+        (last frame wins), exactly as the reference does (:165-175)."""
+        pcl_data = self.load_point_cloud()
+        if len(pcl_data.shape) < 3:
+            pcl_data = pcl_data[np.newaxis, :, :]
+        total_frames = len(pcl_data)
+        for index, pcl in enumerate(pcl_data):
+            pcl, _ = _to_device(pcl, self.DEVICE)
+            pcl = self.standardize_point_cloud(pcl)
+            pcl = self.transform_coordinates(pcl)
+            output_file_path = self._output_path(f'{self.filename}')
+            if total_frames > 1:
+                print(f'  Frame {index+1}/{total_frames}: Rendering...', end=' ', flush=True)
+            else:
+                print('  Rendering...', end=' ', flush=True)
+            rendered_scene = self.render_scene(pcl)
+            print('Saving...', end=' ', flush=True)
+            self.save_scene(output_file_path, rendered_scene)
+            print('Done!')
+
+
+class TrajectoryBallRenderer(PointCloudRenderer):
+    """traj_ball_renderer.py:80 — per-frame sphere render with an animated camera."""
+    PRESET = "traj_ball"
+    WITH_VELOCITY = True
+
+    @staticmethod
+    def compute_color():
+        return np.array([0.3, 0.3, 0.3])
+
+    def process(self, frame_index=0, total_frames=220):
+        """traj_ball_renderer.py:365-398 (velocity trails: SURVEY.md §8f-1, not drawn yet)."""
+        pcl = self.load_point_cloud()
+        if len(pcl.shape) == 3:
+            pcl = pcl[0]
+        pcl, _ = _to_device(pcl, self.DEVICE)
+        pcl = self.standardize_point_cloud(pcl)
+        pcl = self.transform_coordinates(pcl)
+        # the '_b0' suffix for fade frames is inherited by every subclass (traj_ball_renderer.py:376)
+        output_filename = f'frame_{frame_index:04d}_b0' if frame_index > 199 else self.filename
+        output_file_path = self._output_path(output_filename)
+        print('  Rendering...', end=' ', flush=True)
+        rendered_scene = self.render_scene(pcl, frame_index=frame_index, total_frames=total_frames)
+        print('Saving...', end=' ', flush=True)
+        self.save_scene(output_file_path, rendered_scene)
+        print('Done!')
+
+    # ---- batched trajectory path: the whole hot path in one C-ABI call ------------------------
+    def render_trajectory(self, traj, first_frame=0, total_frames=None, want_vis=False, max_batch=8, stretch=True):
+        """traj: (F,N,3|6) array (numpy/CPU tensor -> pcr_render_frames_host with copies overlapped;
+        CUDA tensor -> pcr_render_frames).  Frame f uses compute_camera_position(first_frame+f).
+        stretch=True rescales the 220-frame camera schedule to total_frames."""
+        import torch
+        F, n, cols = traj.shape
+        total = int(total_frames or F)
+        cfg = self.config.for_trajectory(total) if stretch else self.config
+        cams = [cfg.camera(first_frame + f, total, self.width, self.height) for f in range(F)]
+        style = self._style()
+        if self.radius is not None and np.ndim(self.radius) == 0:
+            style.radius = float(self.radius)
+        eng = _engine(self.DEVICE, n, self.width, self.height, batch=min(max_batch, max(F, 1)))
+        if isinstance(traj, torch.Tensor) and traj.is_cuda:
+            radius, rgb = self._per_point(n, traj.device)
+            return eng.render_frames(traj.contiguous(), cams, style, radius=radius, rgb=rgb, want_vis=want_vis)
+        t = torch.as_tensor(traj)
+        radius = None if self.radius is None or np.ndim(self.radius) == 0 else np.ascontiguousarray(self.radius, np.float32)
+        rgb = None if self.user_rgb is None else np.ascontiguousarray(self.user_rgb, np.float32)
+        out_vis = torch.empty((F, self.height, self.width), dtype=torch.int64).pin_memory() if want_vis else None
+        rgba = eng.render_frames_host(t.contiguous(), cams, style, radius_host=radius, rgb_host=rgb, out_vis=out_vis)
+        return (rgba, out_vis) if want_vis else rgba
+
+
+class FixedFrame199Renderer(TrajectoryBallRenderer):
+    """traj_original.py:6 — no x flip (:40-60), fixed camera (-1.8,-1.8,1.8) (:62-66)."""
+    PRESET = "traj_original"
+
+
+class TrajB0Renderer(TrajectoryBallRenderer):
+    """traj_b0.py:6 — dataset batch_0: no x flip, shifted look-at, 3-keyframe camera, big floor."""
+    PRESET = "traj_b0"
+
+
+class TrajB1Renderer(TrajectoryBallRenderer):
+    """traj_b1.py:6 — dataset batch_1."""
+    PRESET = "traj_b1"
+
+
+class TrajectoryRenderer(TrajectoryBallRenderer):
+    """traj_renderer.py:87 — linear dolly camera (:519-527), 256 spp scene; points as spheres."""
+    PRESET = "traj"
+
+    def process(self, frame_index=0, history_pcls=None, total_frames=220):
+        # history_pcls feeds the Catmull-Rom trails (traj_renderer.py:204-396): §8f-2, accepted and unused
+        return super().process(frame_index=frame_index, total_frames=total_frames)
+
+
+class TrajectoryVelRenderer(TrajectoryBallRenderer):
+    """traj_vel_renderer.py:80 — camera as traj_ball (:381-407); velocity attribute available to
+    the colour hook (PCR_COLOR_VELOCITY)."""
+    PRESET = "traj_vel"

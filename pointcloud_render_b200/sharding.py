@@ -1,0 +1,96 @@
+"""Multi-GPU modes of the hot path, one process per GPU over torch.distributed.
+
+The reference renders frames strictly sequentially (traj_ball_renderer.py:461-470) and has no
+collective anywhere; both modes are new:
+
+  frames  — every frame is standardised and rendered independently (traj_ball_renderer.py:373),
+            so a trajectory shards over ranks in contiguous blocks with NO collective.
+  points  — one huge cloud is split by point range.  Two exchange steps exist:
+            C0  all-reduce of {sum xyz | min xyz | max xyz} (9 doubles) so every rank standardises
+                with the global mean / extent (example_renderer.py:96-97);
+            C1  min all-reduce of the packed (depth|id) z-buffer — keys are < 2^63 (the depth is a
+                positive float), so int64 MIN orders them exactly like uint64 MIN: NCCL's
+                ncclAllReduce(ncclInt64, ncclMin) over NVLink, exact and order independent.
+            Shading then runs owner-only and the RGBA8 slices are assembled with a byte MAX.
+
+The collectives run on whatever backend the process group has (nccl on the GPU box, gloo in the
+CPU tests); the compute between them is the pcr C ABI.
+"""
+import numpy as np
+
+
+def frame_shard(n_frames, rank, world):
+    """Contiguous block [start, stop) of frames for `rank` (sizes differ by at most one)."""
+    base, rem = divmod(int(n_frames), int(world))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def point_shard(n_points, rank, world):
+    """Contiguous point range [start, stop) of `rank`; start is also the rank's id_base."""
+    return frame_shard(n_points, rank, world)
+
+
+def finalize_stats(total9, n_total, dtype):
+    """double[9] totals (sum xyz, min xyz, max xyz) -> double[10] (mean xyz, min xyz, max xyz, scale)
+    with the roundings of standardize_point_cloud: mean and extent in the INPUT dtype
+    (example_renderer.py:96-97: np.mean / np.amax(pcl - np.amin(pcl, 0)))."""
+    T = np.dtype(dtype).type
+    total9 = np.asarray(total9, np.float64)
+    out = np.empty(10, np.float64)
+    out[0:3] = [float(T(total9[k] / float(n_total))) for k in range(3)]
+    out[3:9] = total9[3:9]
+    out[9] = max(float(T(T(total9[6 + k]) - T(total9[3 + k]))) for k in range(3))
+    return out
+
+
+def allreduce_stats(partial9, n_local, dtype, group=None):
+    """C0.  partial9: float64 tensor[9] of this rank's shard (pcr_stats_partial).  Returns the
+    global float64 tensor[10] on the same device.  Three tiny all-reduces (sum / min / max)."""
+    import torch
+    import torch.distributed as dist
+    s = partial9[0:3].clone()
+    lo = partial9[3:6].clone()
+    hi = partial9[6:9].clone()
+    n = torch.tensor([float(n_local)], dtype=torch.float64, device=partial9.device)
+    dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(n, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    total = torch.cat([s, lo, hi]).cpu().numpy()
+    stats = finalize_stats(total, int(round(float(n.item()))), dtype)
+    return torch.from_numpy(stats).to(partial9.device)
+
+
+def zmerge_(vis, group=None):
+    """C1.  In-place min all-reduce of the (H,W) int64 view of the uint64 keys."""
+    import torch
+    import torch.distributed as dist
+    assert vis.dtype == torch.int64
+    dist.all_reduce(vis, op=dist.ReduceOp.MIN, group=group)
+    return vis
+
+
+def assemble_image_(rgba, group=None):
+    """Byte-wise MAX of owner-only shaded images (pcr_shade owner_only=1 writes 0 where the
+    winner is not local, and floor/miss pixels only on rank 0)."""
+    import torch.distributed as dist
+    dist.all_reduce(rgba, op=dist.ReduceOp.MAX, group=group)
+    return rgba
+
+
+def render_point_sharded(ctx, pts_local, id_base, cam, style, radius=None, rgb=None, group=None, shade=True):
+    """The whole point-sharded path on one rank: K0 partials -> C0 -> K1 -> K2/K3 -> C1 -> K4(owner)
+    -> byte MAX.  pts_local: (n_local, 3|6) CUDA tensor, this rank's slice of the cloud."""
+    import torch
+    dtype = np.float64 if pts_local.dtype == torch.float64 else np.float32
+    part = ctx.stats_partial(pts_local)
+    stats = allreduce_stats(part, pts_local.shape[0], dtype, group)
+    pos4, attr4 = ctx.standardize_with_stats(pts_local, style, stats, radius=radius, rgb=rgb)
+    vis, _ = ctx.render(pos4, attr4, cam, style, id_base=id_base, shade=False)
+    zmerge_(vis, group)
+    if not shade:
+        return vis, None
+    rgba = ctx.shade(vis, pos4, attr4, cam, style, id_base=id_base, owner_only=True)
+    assemble_image_(rgba, group)
+    return vis, rgba
