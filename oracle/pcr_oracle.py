@@ -25,15 +25,24 @@ KEY_MISS = 0x7F800000FFFFFFFF
 
 
 # --------------------------------------------------------------------------- a1
-def standardize_point_cloud(pcl):
+def standardize_point_cloud(pcl, exact_mean=False):
     """example_renderer.py:94-98 (3 cols) / traj_ball_renderer.py:190-202 (3|6 cols).
 
     center = mean, scale = largest axis extent (one scalar), arithmetic in the input
     dtype, cast to f32 last; velocity columns are cast to f32 and passed through unscaled.
+
+    exact_mean=False is the reference verbatim: np.mean(axis=0) of an (N,3) array is a plain
+    SEQUENTIAL sum in the input dtype (verified: it equals a python loop `acc = acc + row`), so
+    for float32 input its error grows with N and with |mean|/extent (2e-5 at N=1e5, mean 5).
+    exact_mean=True is the order-independent definition the CUDA path implements: the mean is
+    summed in float64 and rounded once to the input dtype; everything else is unchanged.
     """
     pcl = np.asarray(pcl)
     positions = pcl[:, :3]
-    center = np.mean(positions, axis=0)
+    if exact_mean:
+        center = (np.sum(positions, axis=0, dtype=np.float64) / positions.shape[0]).astype(positions.dtype)
+    else:
+        center = np.mean(positions, axis=0)
     scale = np.amax(positions - np.amin(positions, axis=0))
     normalized = ((positions - center) / scale).astype(np.float32)
     if pcl.shape[1] == 6:
