@@ -49,6 +49,10 @@ struct pcr_ctx {
     unsigned int* done = nullptr;
     unsigned int *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *pairs = nullptr, *overflow = nullptr;
     unsigned long long* stat_pairs = nullptr;
+    unsigned int *item_count = nullptr, *item_next = nullptr;
+    uint2* items = nullptr;
+    int item_cap = 0;
+    int smem_optin = 48 * 1024;       // max dynamic shared memory per block (opt-in)
     uint64_t* vis = nullptr;          // lazily allocated when the caller passes d_vis == NULL
     FrameDev* d_frames = nullptr;
     FrameDev* h_frames = nullptr;     // pinned ring: RING_SLOTS x max_batch
@@ -181,6 +185,7 @@ BinDev bin_of(pcr_ctx* c)
     BinDev b;
     b.counts = c->counts; b.offsets = c->offsets; b.cursor = c->cursor; b.pairs = c->pairs;
     b.overflow = c->overflow; b.stat_pairs = c->stat_pairs; b.tiles_cap = c->tiles_cap; b.pair_cap = c->pair_cap;
+    b.item_count = c->item_count; b.item_next = c->item_next; b.items = c->items; b.item_cap = c->item_cap;
     return b;
 }
 
@@ -235,18 +240,29 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
 {
     BinDev bin = bin_of(ctx);
     const int tiles = ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    // K2 blocks own contiguous point chunks and histogram their pairs in shared memory when the
+    // tile count allows it (count: 4 B/tile, scatter: 8 B/tile)
+    const int use_smem = (size_t)tiles * 8 <= (size_t)ctx->smem_optin ? 1 : 0;
+    const int resident = ctx->num_sms * (2048 / BIN_THREADS);
+    unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((n + 4095) / 4096, std::max(1, resident / nb)));
+    if (!use_smem) gx = (unsigned)std::max<long long>(1, (n + BIN_THREADS * 4 - 1) / (BIN_THREADS * 4));
     if (n > 0) {
-        dim3 grid((unsigned)((n + 255) / 256), nb);
-        LAUNCH(KID_PROJECT, stream, k_project_count<<<grid, 256, 0, stream>>>(pos, n, in_stride, ctx->d_frames, ctx->sph, ctx->rect, ctx->max_points, bin));
+        dim3 grid(gx, nb);
+        LAUNCH(KID_PROJECT, stream, k_project_count<<<grid, BIN_THREADS, use_smem ? tiles * 4 : 0, stream>>>(
+            pos, n, in_stride, ctx->d_frames, ctx->sph, ctx->rect, ctx->max_points, bin, use_smem));
     }
     LAUNCH(KID_SCAN, stream, k_scan_tiles<<<nb, 1024, 0, stream>>>(ctx->d_frames, bin));
     if (n > 0) {
-        dim3 grid((unsigned)((n + 255) / 256), nb);
-        LAUNCH(KID_SCATTER, stream, k_scatter<<<grid, 256, 0, stream>>>(n, ctx->d_frames, ctx->rect, ctx->max_points, bin));
+        dim3 grid(gx, nb);
+        LAUNCH(KID_SCATTER, stream, k_scatter<<<grid, BIN_THREADS, use_smem ? tiles * 8 : 0, stream>>>(
+            n, ctx->d_frames, ctx->rect, ctx->max_points, bin, use_smem, (unsigned long long*)vis, vis_stride));
     }
     {
-        dim3 grid(tiles, nb);
-        LAUNCH(KID_RASTER, stream, k_raster_tiles<<<grid, RASTER_THREADS, 0, stream>>>(ctx->d_frames, st, ctx->sph, ctx->rect, ctx->max_points, bin, id_base, vis, vis_stride));
+        // persistent raster: CTAs pull (tile, <= ITEM_SPHERES spheres) items from per-frame queues
+        const int ctas = ctx->num_sms * (2048 / RASTER_THREADS);
+        dim3 grid((unsigned)std::max(1, std::min(ctas / nb, tiles)), nb);
+        LAUNCH(KID_RASTER, stream, k_raster_tiles<<<grid, RASTER_THREADS, 0, stream>>>(
+            ctx->d_frames, st, ctx->sph, ctx->rect, ctx->max_points, bin, id_base, (unsigned long long*)vis, vis_stride, nb));
     }
     if (n > 0) {
         dim3 grid(ctx->num_sms * 4, nb);
@@ -299,11 +315,17 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     ctx->pair_cap = pair_capacity > 0 ? pair_capacity : 8 * max_points + 65536;
     if (ctx->pair_cap > 0xFFFFFFF0ll) ctx->pair_cap = 0xFFFFFFF0ll;
     ctx->tiles_cap = ((max_w + TILE - 1) / TILE) * ((max_h + TILE - 1) / TILE);
+    ctx->item_cap = ctx->tiles_cap + (int)(ctx->pair_cap / ITEM_SPHERES) + 1;
     const size_t B = (size_t)max_batch, N = (size_t)max_points, Tn = (size_t)ctx->tiles_cap;
     cudaError_t e = cudaSetDevice(device);
     cudaDeviceProp prop;
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
-    if (e == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
+    if (e == cudaSuccess) {
+        ctx->num_sms = prop.multiProcessorCount;
+        ctx->smem_optin = (int)std::min<size_t>(prop.sharedMemPerBlockOptin, 200 * 1024);
+        e = cudaFuncSetAttribute(k_project_count, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+    }
 #define ALLOC(ptr, bytes) if (e == cudaSuccess) e = cudaMalloc((void**)&(ptr), (bytes))
     ALLOC(ctx->pos, sizeof(float4) * B * N);
     ALLOC(ctx->attr, sizeof(float4) * B * N);
@@ -318,6 +340,9 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     ALLOC(ctx->pairs, sizeof(unsigned int) * B * (size_t)ctx->pair_cap);
     ALLOC(ctx->overflow, sizeof(unsigned int) * B);
     ALLOC(ctx->stat_pairs, sizeof(unsigned long long) * B);
+    ALLOC(ctx->item_count, sizeof(unsigned int) * B);
+    ALLOC(ctx->item_next, sizeof(unsigned int) * B);
+    ALLOC(ctx->items, sizeof(uint2) * B * (size_t)ctx->item_cap);
     ALLOC(ctx->d_frames, sizeof(FrameDev) * B);
 #undef ALLOC
     if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_frames, sizeof(FrameDev) * B * RING_SLOTS);
@@ -343,7 +368,7 @@ void pcr_destroy(pcr_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     void* frees[] = {ctx->pos, ctx->attr, ctx->sph, ctx->rect, ctx->partials, ctx->stats, ctx->done, ctx->counts, ctx->offsets,
-                     ctx->cursor, ctx->pairs, ctx->overflow, ctx->stat_pairs, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
+                     ctx->cursor, ctx->pairs, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
                      ctx->stage_rgba[0], ctx->stage_rgba[1], ctx->stage_vis[0], ctx->stage_vis[1], ctx->stage_radius, ctx->stage_rgb};
     for (void* p : frees) if (p) cudaFree(p);
     if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
