@@ -32,6 +32,8 @@ def command(verbose=False):
         cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    for flag in os.environ.get("PCR_NVCC_FLAGS", "").split():      # e.g. -DPCR_RASTER_STATS for diagnostics builds
+        cmd.insert(1, flag)
     return cmd
 
 

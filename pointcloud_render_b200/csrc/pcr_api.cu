@@ -23,9 +23,10 @@ constexpr int RING_SLOTS = 4;
 constexpr int MAX_STAT_BLOCKS = 1184;   // 148 SMs x 8
 
 enum KernelId { KID_STATS = 0, KID_TRANSFORM, KID_PROJECT, KID_SCAN, KID_SCATTER, KID_RASTER, KID_RASTER_NAIVE, KID_SHADE,
-                KID_ZMIN, KID_AXIS, KID_COUNT };
+                KID_ZMIN, KID_AXIS, KID_FILL, KID_COUNT };
 const char* const kKernelNames[KID_COUNT] = {"k_stats", "k_transform", "k_project_count", "k_scan_tiles", "k_scatter",
-                                             "k_raster_tiles", "k_raster_naive", "k_shade", "k_zmin", "k_axis_transform"};
+                                             "k_raster_tiles", "k_raster_naive", "k_shade", "k_zmin", "k_axis_transform",
+                                             "k_fill_tiles"};
 constexpr size_t PROF_MAX_RECORDS = 1 << 16;
 
 struct ProfRec { int kid; cudaEvent_t a, b; };
@@ -214,10 +215,12 @@ int launch_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, long long n, int
     int blocks = (int)std::min<long long>((n + 256 * 8 - 1) / (256 * 8), MAX_STAT_BLOCKS);
     blocks = std::max(blocks, 1);
     dim3 grid(blocks, nb);
+    // float4 streaming needs 3 columns and every frame base on a 16-byte boundary
+    const int vec = !in_is_f64 && cols == 3 && ((uintptr_t)d_in % 16 == 0) && (nb == 1 || (frame_stride * 4) % 16 == 0);
     if (in_is_f64)
-        LAUNCH(KID_STATS, stream, k_stats<double><<<grid, 256, 0, stream>>>((const double*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, ctx->done, finalize));
+        LAUNCH(KID_STATS, stream, k_stats<double><<<grid, 256, 0, stream>>>((const double*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, ctx->done, finalize, 0));
     else
-        LAUNCH(KID_STATS, stream, k_stats<float><<<grid, 256, 0, stream>>>((const float*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, ctx->done, finalize));
+        LAUNCH(KID_STATS, stream, k_stats<float><<<grid, 256, 0, stream>>>((const float*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, ctx->done, finalize, vec));
     return PCR_OK;
 }
 
@@ -255,7 +258,12 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
     if (n > 0) {
         dim3 grid(gx, nb);
         LAUNCH(KID_SCATTER, stream, k_scatter<<<grid, BIN_THREADS, use_smem ? tiles * 8 : 0, stream>>>(
-            n, ctx->d_frames, ctx->rect, ctx->max_points, bin, use_smem, (unsigned long long*)vis, vis_stride));
+            n, ctx->d_frames, ctx->rect, ctx->max_points, bin, use_smem));
+    }
+    {
+        // floor keys of empty tiles, all-ones preset of split tiles
+        dim3 grid((unsigned)std::max(1, std::min((tiles + 7) / 8, ctx->num_sms * 8 / nb)), nb);
+        LAUNCH(KID_FILL, stream, k_fill_tiles<<<grid, 256, 0, stream>>>(ctx->d_frames, st, bin, (unsigned long long*)vis, vis_stride));
     }
     {
         // persistent raster: CTAs pull (tile, <= ITEM_SPHERES spheres) items from per-frame queues
@@ -339,7 +347,7 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     ALLOC(ctx->cursor, sizeof(unsigned int) * B * Tn);
     ALLOC(ctx->pairs, sizeof(unsigned int) * B * (size_t)ctx->pair_cap);
     ALLOC(ctx->overflow, sizeof(unsigned int) * B);
-    ALLOC(ctx->stat_pairs, sizeof(unsigned long long) * B);
+    ALLOC(ctx->stat_pairs, sizeof(unsigned long long) * (B + 16));
     ALLOC(ctx->item_count, sizeof(unsigned int) * B);
     ALLOC(ctx->item_next, sizeof(unsigned int) * B);
     ALLOC(ctx->items, sizeof(uint2) * B * (size_t)ctx->item_cap);
@@ -349,7 +357,7 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     if (e == cudaSuccess) e = cudaMemset(ctx->counts, 0, sizeof(unsigned int) * B * Tn);
     if (e == cudaSuccess) e = cudaMemset(ctx->done, 0, sizeof(unsigned int) * B);
     if (e == cudaSuccess) e = cudaMemset(ctx->overflow, 0, sizeof(unsigned int) * B);
-    if (e == cudaSuccess) e = cudaMemset(ctx->stat_pairs, 0, sizeof(unsigned long long) * B);
+    if (e == cudaSuccess) e = cudaMemset(ctx->stat_pairs, 0, sizeof(unsigned long long) * (B + 16));
     for (int k = 0; k < RING_SLOTS && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&ctx->ring_ev[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -551,9 +559,12 @@ int pcr_render_frames_host(pcr_ctx* ctx, const void* h_in, int in_is_f64, int64_
     const float *d_radius = nullptr, *d_rgb = nullptr;
     if (h_radius) { CK(cudaMemcpyAsync(ctx->stage_radius, h_radius, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->s_comp)); d_radius = ctx->stage_radius; }
     if (h_rgb) { CK(cudaMemcpyAsync(ctx->stage_rgb, h_rgb, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->s_comp)); d_rgb = ctx->stage_rgb; }
+    // chunks of at most B frames, but at least ~4 chunks per call so that the H2D copy of chunk
+    // k+1, the kernels of chunk k and the D2H copy of chunk k-1 overlap even for short calls
+    const int C = std::max(1, std::min(B, (n_frames + 3) / 4));
     int chunk = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += B, ++chunk) {
-        const int nb = std::min(B, n_frames - f0);
+    for (int f0 = 0; f0 < n_frames; f0 += C, ++chunk) {
+        const int nb = std::min(C, n_frames - f0);
         const int k = chunk & 1;
         if (chunk >= 2) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[k], 0));   // input slot free again
         CK(cudaMemcpyAsync(ctx->stage_in[k], (const char*)h_in + (size_t)f0 * frame_bytes, (size_t)nb * frame_bytes,
@@ -617,6 +628,14 @@ int pcr_counters(pcr_ctx* ctx, int64_t out[4], void* stream)
     std::vector<unsigned int> ov(ctx->max_batch);
     CK(cudaMemcpy(&pairs, ctx->stat_pairs, sizeof(pairs), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(ov.data(), ctx->overflow, sizeof(unsigned int) * ctx->max_batch, cudaMemcpyDeviceToHost));
+#ifdef PCR_RASTER_STATS
+    {
+        unsigned long long dbg[16];
+        CK(cudaMemcpy(dbg, ctx->stat_pairs, sizeof(dbg), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[pcr stats] warp-candidates %llu  cull-iterations %llu  box-pass %llu\n", dbg[8], dbg[9], dbg[10]);
+        CK(cudaMemset(ctx->stat_pairs + 8, 0, 8 * sizeof(unsigned long long)));
+    }
+#endif
     long long nov = 0;
     for (unsigned int v : ov) nov += v != 0;
     out[0] = ctx->launches; out[1] = (int64_t)pairs; out[2] = nov; out[3] = 0;
