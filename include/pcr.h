@@ -213,6 +213,14 @@ int pcr_standardize_with_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, in
  * out[2] = frames that overflowed pair_capacity, out[3] = spheres culled (last frame). */
 int pcr_counters(pcr_ctx* ctx, int64_t out[4], void* stream);
 
+/* Occlusion pre-pass of pcr_render / pcr_render_frames.  Dense clouds bury most spheres (depth
+ * complexity in the hundreds at 1 M points): the pre-pass rasterises every step-th point, builds
+ * a per-8x4-pixel farthest-depth map, and the main pass drops every sphere that lies entirely
+ * behind it before it is binned.  Purely a work-skipping device: the keys are identical.
+ *   mode -1: automatic (on when n >= min_points; default min_points 131072), 0: off, 1: always
+ *   step  0: keep (default 16) ; min_points 0: keep */
+int pcr_set_occlusion(pcr_ctx* ctx, int mode, int step, int64_t min_points);
+
 /* Per-kernel timing.  While enabled, every kernel launch is bracketed by two CUDA events on the
  * launching stream.  pcr_profile_read waits for the recorded events, writes the summed
  * milliseconds and launch counts per kernel id (index k <-> pcr_kernel_name(k)), clears the

@@ -22,7 +22,7 @@ SYMBOLS = (
     "pcr_abi_version", "pcr_create", "pcr_destroy", "pcr_last_error", "pcr_camera_frame",
     "pcr_standardize", "pcr_render", "pcr_shade", "pcr_render_frames", "pcr_render_frames_host",
     "pcr_zmin", "pcr_zmerge_nccl", "pcr_stats_partial", "pcr_standardize_with_stats", "pcr_counters",
-    "pcr_transform_coordinates", "pcr_profile", "pcr_profile_read", "pcr_kernel_name",
+    "pcr_transform_coordinates", "pcr_profile", "pcr_profile_read", "pcr_kernel_name", "pcr_set_occlusion",
 )
 
 
@@ -83,6 +83,7 @@ def load_library():
     L.pcr_standardize_with_stats.argtypes = [vp, vp, i32, i64, i32, vp, vp, styp, vp, vp, vp, vp, vp]
     L.pcr_counters.argtypes = [vp, ctypes.POINTER(i64), vp]
     L.pcr_transform_coordinates.argtypes = [vp, vp, i64, i32, i32, ctypes.c_float, vp, vp]
+    L.pcr_set_occlusion.argtypes = [vp, i32, i32, i64]
     L.pcr_profile.argtypes = [vp, i32]
     L.pcr_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), i32]
     L.pcr_kernel_name.argtypes = [i32]
@@ -281,6 +282,10 @@ class Context:
     def zmin_(self, dst, src, stream=None):
         self._check(self.lib.pcr_zmin(self.handle, _ptr(dst), _ptr(src), dst.numel(), _stream_ptr(stream)))
         return dst
+
+    def set_occlusion(self, mode=-1, step=0, min_points=0):
+        """Occlusion pre-pass: mode -1 auto, 0 off, 1 always (see pcr_set_occlusion)."""
+        self._check(self.lib.pcr_set_occlusion(self.handle, int(mode), int(step), int(min_points)))
 
     def profile(self, enable=True):
         self._check(self.lib.pcr_profile(self.handle, int(bool(enable))))

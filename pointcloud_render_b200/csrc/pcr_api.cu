@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -22,10 +23,10 @@ namespace {
 constexpr int RING_SLOTS = 4;
 constexpr int MAX_STAT_BLOCKS = 1184;   // 148 SMs x 8
 
-enum KernelId { KID_STATS = 0, KID_TRANSFORM, KID_PROJECT, KID_SCAN, KID_SCATTER, KID_RASTER, KID_RASTER_NAIVE, KID_SHADE,
+enum KernelId { KID_STATS = 0, KID_TRANSFORM, KID_PROJECT, KID_SCAN, KID_SCATTER, KID_RASTER, KID_HIZ, KID_SHADE,
                 KID_ZMIN, KID_AXIS, KID_FILL, KID_COUNT };
 const char* const kKernelNames[KID_COUNT] = {"k_stats", "k_transform", "k_project_count", "k_scan_tiles", "k_scatter",
-                                             "k_raster_tiles", "k_raster_naive", "k_shade", "k_zmin", "k_axis_transform",
+                                             "k_raster_tiles", "k_hiz", "k_shade", "k_zmin", "k_axis_transform",
                                              "k_fill_tiles"};
 constexpr size_t PROF_MAX_RECORDS = 1 << 16;
 
@@ -54,6 +55,11 @@ struct pcr_ctx {
     uint2* items = nullptr;
     int item_cap = 0;
     int smem_optin = 48 * 1024;       // max dynamic shared memory per block (opt-in)
+    unsigned int* hz = nullptr;       // [max_batch][hz_cap] farthest pre-pass depth per 8x4 pixel block
+    int hz_cap = 0;
+    int occlusion = -1;               // -1 auto (n >= occlusion_min_points), 0 off, 1 always
+    int occlusion_step = 16;          // the pre-pass rasterises every step-th point
+    long long occlusion_min_points = 1 << 17;
     uint64_t* vis = nullptr;          // lazily allocated when the caller passes d_vis == NULL
     FrameDev* d_frames = nullptr;
     FrameDev* h_frames = nullptr;     // pinned ring: RING_SLOTS x max_batch
@@ -247,35 +253,52 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
     // tile count allows it (count: 4 B/tile, scatter: 8 B/tile)
     const int use_smem = (size_t)tiles * 8 <= (size_t)ctx->smem_optin ? 1 : 0;
     const int resident = ctx->num_sms * (2048 / BIN_THREADS);
-    unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((n + 4095) / 4096, std::max(1, resident / nb)));
-    if (!use_smem) gx = (unsigned)std::max<long long>(1, (n + BIN_THREADS * 4 - 1) / (BIN_THREADS * 4));
-    if (n > 0) {
-        dim3 grid(gx, nb);
-        LAUNCH(KID_PROJECT, stream, k_project_count<<<grid, BIN_THREADS, use_smem ? tiles * 4 : 0, stream>>>(
-            pos, n, in_stride, ctx->d_frames, ctx->sph, ctx->rect, ctx->max_points, bin, use_smem));
-    }
-    LAUNCH(KID_SCAN, stream, k_scan_tiles<<<nb, 1024, 0, stream>>>(ctx->d_frames, bin));
-    if (n > 0) {
-        dim3 grid(gx, nb);
-        LAUNCH(KID_SCATTER, stream, k_scatter<<<grid, BIN_THREADS, use_smem ? tiles * 8 : 0, stream>>>(
-            n, ctx->d_frames, ctx->rect, ctx->max_points, bin, use_smem));
-    }
-    {
-        // floor keys of empty tiles, all-ones preset of split tiles
-        dim3 grid((unsigned)std::max(1, std::min((tiles + 7) / 8, ctx->num_sms * 8 / nb)), nb);
-        LAUNCH(KID_FILL, stream, k_fill_tiles<<<grid, 256, 0, stream>>>(ctx->d_frames, st, bin, (unsigned long long*)vis, vis_stride));
-    }
-    {
-        // persistent raster: CTAs pull (tile, <= ITEM_SPHERES spheres) items from per-frame queues
-        const int ctas = ctx->num_sms * (2048 / RASTER_THREADS);
-        dim3 grid((unsigned)std::max(1, std::min(ctas / nb, tiles)), nb);
-        LAUNCH(KID_RASTER, stream, k_raster_tiles<<<grid, RASTER_THREADS, 0, stream>>>(
-            ctx->d_frames, st, ctx->sph, ctx->rect, ctx->max_points, bin, id_base, (unsigned long long*)vis, vis_stride, nb));
-    }
-    if (n > 0) {
-        dim3 grid(ctx->num_sms * 4, nb);
-        LAUNCH(KID_RASTER_NAIVE, stream, k_raster_naive<<<grid, 256, 0, stream>>>(n, ctx->d_frames, ctx->sph, ctx->rect, ctx->max_points, bin, id_base,
-                                                                                  (unsigned long long*)vis, vis_stride));
+    const int raster_ctas = ctx->num_sms * (2048 / RASTER_THREADS);
+    unsigned long long* v = (unsigned long long*)vis;
+
+    // one binning + raster pass over `np` spheres (sphere i = point i*step)
+    auto pass = [&](long long np, int step, const unsigned int* hz, int seeded) -> int {
+        unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((np + 4095) / 4096, std::max(1, resident / nb)));
+        if (!use_smem) gx = (unsigned)std::max<long long>(1, (np + BIN_THREADS * 4 - 1) / (BIN_THREADS * 4));
+        if (np > 0) {
+            dim3 grid(gx, nb);
+            LAUNCH(KID_PROJECT, stream, k_project_count<<<grid, BIN_THREADS, use_smem ? tiles * 4 : 0, stream>>>(
+                pos, np, in_stride, step, ctx->d_frames, ctx->sph, ctx->rect, ctx->max_points, bin, use_smem, hz, ctx->hz_cap));
+        }
+        LAUNCH(KID_SCAN, stream, k_scan_tiles<<<nb, 1024, 0, stream>>>(ctx->d_frames, bin));
+        if (np > 0) {
+            dim3 grid(gx, nb);
+            LAUNCH(KID_SCATTER, stream, k_scatter<<<grid, BIN_THREADS, use_smem ? tiles * 8 : 0, stream>>>(
+                np, ctx->d_frames, ctx->rect, ctx->max_points, bin, use_smem));
+        }
+        if (!seeded) {
+            // floor keys of empty tiles, all-ones preset of split tiles
+            dim3 grid((unsigned)std::max(1, std::min((tiles + 7) / 8, ctx->num_sms * 8 / nb)), nb);
+            LAUNCH(KID_FILL, stream, k_fill_tiles<<<grid, 256, 0, stream>>>(ctx->d_frames, st, bin, v, vis_stride));
+        }
+        if (np > 0) {
+            // persistent raster: CTAs pull (tile, <= ITEM_SPHERES spheres) items from per-frame queues
+            dim3 grid((unsigned)std::max(1, std::min(raster_ctas / nb, tiles)), nb);
+            LAUNCH(KID_RASTER, stream, k_raster_tiles<<<grid, RASTER_THREADS, 0, stream>>>(
+                ctx->d_frames, st, ctx->sph, ctx->rect, ctx->max_points, bin, id_base, (uint32_t)step, v, vis_stride, nb, np, seeded));
+        }
+        return PCR_OK;
+    };
+
+    const bool occl = ctx->occlusion > 0 || (ctx->occlusion < 0 && n >= ctx->occlusion_min_points);
+    if (occl && n > ctx->occlusion_step) {
+        // occluder pre-pass (every step-th point, true ids) -> Hi-Z -> main pass seeded with its keys
+        const int step = ctx->occlusion_step;
+        int rc = pass((n + step - 1) / step, step, nullptr, 0);
+        if (rc) return rc;
+        const int hzn = ((W + HZ_W - 1) / HZ_W) * ((H + HZ_H - 1) / HZ_H);
+        dim3 grid((unsigned)((hzn + 255) / 256), nb);
+        LAUNCH(KID_HIZ, stream, k_hiz<<<grid, 256, 0, stream>>>(ctx->d_frames, v, vis_stride, ctx->hz, ctx->hz_cap));
+        rc = pass(n, 1, ctx->hz, 1);
+        if (rc) return rc;
+    } else {
+        int rc = pass(n, 1, nullptr, 0);
+        if (rc) return rc;
     }
     if (rgba) {
         dim3 grid((unsigned)(((long long)W * H + 255) / 256), nb);
@@ -324,6 +347,9 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     if (ctx->pair_cap > 0xFFFFFFF0ll) ctx->pair_cap = 0xFFFFFFF0ll;
     ctx->tiles_cap = ((max_w + TILE - 1) / TILE) * ((max_h + TILE - 1) / TILE);
     ctx->item_cap = ctx->tiles_cap + (int)(ctx->pair_cap / ITEM_SPHERES) + 1;
+    ctx->hz_cap = ((max_w + HZ_W - 1) / HZ_W) * ((max_h + HZ_H - 1) / HZ_H);
+    if (const char* e = getenv("PCR_OCCLUSION")) ctx->occlusion = atoi(e);
+    if (const char* e = getenv("PCR_OCCLUSION_STEP")) ctx->occlusion_step = std::max(2, atoi(e));
     const size_t B = (size_t)max_batch, N = (size_t)max_points, Tn = (size_t)ctx->tiles_cap;
     cudaError_t e = cudaSetDevice(device);
     cudaDeviceProp prop;
@@ -351,6 +377,7 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     ALLOC(ctx->item_count, sizeof(unsigned int) * B);
     ALLOC(ctx->item_next, sizeof(unsigned int) * B);
     ALLOC(ctx->items, sizeof(uint2) * B * (size_t)ctx->item_cap);
+    ALLOC(ctx->hz, sizeof(unsigned int) * B * (size_t)ctx->hz_cap);
     ALLOC(ctx->d_frames, sizeof(FrameDev) * B);
 #undef ALLOC
     if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_frames, sizeof(FrameDev) * B * RING_SLOTS);
@@ -376,7 +403,7 @@ void pcr_destroy(pcr_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     void* frees[] = {ctx->pos, ctx->attr, ctx->sph, ctx->rect, ctx->partials, ctx->stats, ctx->done, ctx->counts, ctx->offsets,
-                     ctx->cursor, ctx->pairs, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
+                     ctx->cursor, ctx->pairs, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
                      ctx->stage_rgba[0], ctx->stage_rgba[1], ctx->stage_vis[0], ctx->stage_vis[1], ctx->stage_radius, ctx->stage_rgb};
     for (void* p : frees) if (p) cudaFree(p);
     if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
@@ -667,6 +694,16 @@ int pcr_profile_read(pcr_ctx* ctx, double* ms_out, int64_t* count_out, int capac
     }
     ctx->prof.clear();
     return KID_COUNT;
+}
+
+int pcr_set_occlusion(pcr_ctx* ctx, int mode, int step, int64_t min_points)
+{
+    if (!ctx) return PCR_ERR_INVALID;
+    if (mode < -1 || mode > 1 || (step != 0 && step < 2)) return fail(ctx, PCR_ERR_INVALID, "pcr_set_occlusion: mode in {-1,0,1}, step >= 2");
+    ctx->occlusion = mode;
+    if (step) ctx->occlusion_step = step;
+    if (min_points > 0) ctx->occlusion_min_points = min_points;
+    return PCR_OK;
 }
 
 const char* pcr_kernel_name(int kernel_id) { return kernel_id >= 0 && kernel_id < KID_COUNT ? kKernelNames[kernel_id] : ""; }

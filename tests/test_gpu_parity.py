@@ -28,10 +28,14 @@ def ref_atol(x):
     return 2.0 ** -23 + 2.0 * np.sqrt(len(x)) * eps * float(np.abs(x).max()) / scale
 
 
-@pytest.fixture(scope="module")
-def ctx(lib):
+@pytest.fixture(scope="module", params=["auto", "occlusion-always"])
+def ctx(lib, request):
+    """Every test runs twice: default settings (occlusion pre-pass only for n >= 131072) and with
+    the pre-pass forced on for every cloud size (step 4 so that even tiny clouds exercise it)."""
     assert torch.cuda.is_available(), "gpu tests need a CUDA device"
     c = _native.Context(device=0, max_points=1 << 20, max_w=1920, max_h=1080, max_batch=4)
+    if request.param == "occlusion-always":
+        c.set_occlusion(mode=1, step=4)
     yield c
     c.close()
 
@@ -330,6 +334,32 @@ def test_headline_size_properties(ctx, orc):
         ids = _native.keys_to_ids(vis)
         assert np.all((ids < n) | (ids >= 0xFFFFFFFE))
         assert ctx.counters()["overflow_frames"] == 0
+
+
+@pytest.mark.parametrize("step", [2, 16, 64])
+def test_occlusion_prepass_never_changes_a_key(lib, orc, step):
+    """The pre-pass only skips work: keys and images are identical with it on, off, and for any
+    subsampling step — also when the pre-pass or the main pass overflows pair_capacity."""
+    n, W, H = 400_000, 1024, 768
+    cfg = PRESETS["traj_ball"]
+    p = orc.transform_coordinates(orc.standardize_point_cloud(synthetic.cloud(n, "gauss", 9)), True)
+    pos4 = dev(np.concatenate([p, np.full((n, 1), 0.01, np.float32)], axis=1))
+    attr4 = dev(np.full((n, 4), 0.3, np.float32))
+    cam, style = cfg.camera(120, 220, W, H), cfg.style()
+    results = []
+    for mode, cap in ((0, 0), (1, 0), (1, 60_000)):
+        c = _native.Context(device=0, max_points=n, max_w=W, max_h=H, max_batch=1, pair_capacity=cap)
+        try:
+            c.set_occlusion(mode=mode, step=step)
+            vis, rgba = c.render(pos4, attr4, cam, style)
+            results.append((vis.clone(), rgba.clone(), c.counters()))
+        finally:
+            c.close()
+    assert torch.equal(results[0][0], results[1][0]) and torch.equal(results[0][1], results[1][1])
+    assert torch.equal(results[0][0], results[2][0]) and torch.equal(results[0][1], results[2][1])
+    assert results[1][2]["pairs_last_frame"] < 0.5 * results[0][2]["pairs_last_frame"]     # it did skip work
+    want = orc.visibility(pos4.cpu().numpy(), orc_frame(orc, cfg, 120, 220, W, H), orc_scene(orc, cfg))
+    np.testing.assert_array_equal(keys(results[1][0]), want)
 
 
 def test_facade_end_to_end(tmp_path, orc):
