@@ -25,7 +25,6 @@ def nvcc_path():
 
 def command(verbose=False):
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "--fmad=false",                      # VA-1: only the fmaf() written in the source is fused
            "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall",
            "-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB] + SOURCES + ["-ldl"]
     if os.path.isfile("/usr/bin/g++"):

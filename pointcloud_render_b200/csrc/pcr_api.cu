@@ -253,19 +253,19 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
     // tile count allows it (count: 4 B/tile, scatter: 8 B/tile)
     const int use_smem = (size_t)tiles * 8 <= (size_t)ctx->smem_optin ? 1 : 0;
     const int resident = ctx->num_sms * (2048 / BIN_THREADS);
-    const int raster_ctas = ctx->num_sms * (2048 / RASTER_THREADS);
+    const int raster_ctas = ctx->num_sms * 4;          // k_raster_tiles: 4 CTAs of 256 threads resident per SM (register bound)
     unsigned long long* v = (unsigned long long*)vis;
 
     // one binning + raster pass over `np` spheres (sphere i = point i*step)
     auto pass = [&](long long np, int step, const unsigned int* hz, int seeded) -> int {
-        unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((np + 4095) / 4096, std::max(1, resident / nb)));
+        unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((np + 2047) / 2048, std::max(1, 2 * resident / nb)));
         if (!use_smem) gx = (unsigned)std::max<long long>(1, (np + BIN_THREADS * 4 - 1) / (BIN_THREADS * 4));
         if (np > 0) {
             dim3 grid(gx, nb);
             LAUNCH(KID_PROJECT, stream, k_project_count<<<grid, BIN_THREADS, use_smem ? tiles * 4 : 0, stream>>>(
                 pos, np, in_stride, step, ctx->d_frames, ctx->sph, ctx->rect, ctx->max_points, bin, use_smem, hz, ctx->hz_cap));
         }
-        LAUNCH(KID_SCAN, stream, k_scan_tiles<<<nb, 1024, 0, stream>>>(ctx->d_frames, bin));
+        LAUNCH(KID_SCAN, stream, k_scan_tiles<<<nb, 1024, 0, stream>>>(ctx->d_frames, bin, np));
         if (np > 0) {
             dim3 grid(gx, nb);
             LAUNCH(KID_SCATTER, stream, k_scatter<<<grid, BIN_THREADS, use_smem ? tiles * 8 : 0, stream>>>(
@@ -273,12 +273,12 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         }
         if (!seeded) {
             // floor keys of empty tiles, all-ones preset of split tiles
-            dim3 grid((unsigned)std::max(1, std::min((tiles + 7) / 8, ctx->num_sms * 8 / nb)), nb);
+            dim3 grid((unsigned)std::max(1, std::min((tiles + 7) / 8, ctx->num_sms * 32 / nb)), nb);
             LAUNCH(KID_FILL, stream, k_fill_tiles<<<grid, 256, 0, stream>>>(ctx->d_frames, st, bin, v, vis_stride));
         }
         if (np > 0) {
             // persistent raster: CTAs pull (tile, <= ITEM_SPHERES spheres) items from per-frame queues
-            dim3 grid((unsigned)std::max(1, std::min(raster_ctas / nb, tiles)), nb);
+            dim3 grid((unsigned)std::max(1, std::min(raster_ctas, tiles * nb)));
             LAUNCH(KID_RASTER, stream, k_raster_tiles<<<grid, RASTER_THREADS, 0, stream>>>(
                 ctx->d_frames, st, ctx->sph, ctx->rect, ctx->max_points, bin, id_base, (uint32_t)step, v, vis_stride, nb, np, seeded));
         }
@@ -301,7 +301,7 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         if (rc) return rc;
     }
     if (rgba) {
-        dim3 grid((unsigned)(((long long)W * H + 255) / 256), nb);
+        dim3 grid((unsigned)((W + 63) / 64), (unsigned)((H + 3) / 4), nb);
         LAUNCH(KID_SHADE, stream, k_shade<<<grid, 256, 0, stream>>>(ctx->d_frames, st, vis, vis_stride, pos, attr, in_stride, n, id_base, owner_only,
                                                                     (uint32_t*)rgba, rgba_stride));
     }
@@ -335,7 +335,7 @@ int pcr_camera_frame(const pcr_camera* cam, pcr_frame* out) { return camera_fram
 
 int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max_h, int max_batch, int64_t pair_capacity)
 {
-    if (!out || max_points < 1 || max_points > 0xFFFFFFF0ll || max_w < 1 || max_h < 1 || max_w > 65535 || max_h > 65535 || max_batch < 1)
+    if (!out || max_points < 1 || max_points > 0xFFFFFFF0ll || max_w < 1 || max_h < 1 || max_w > 65535 || max_h > 65535 || max_batch < 1 || max_batch > 64)
         return PCR_ERR_INVALID;
     *out = nullptr;
     int ndev = 0;
@@ -504,7 +504,7 @@ int pcr_shade(pcr_ctx* ctx, const uint64_t* d_vis, const float* d_pos, const flo
     rc = upload_frames(ctx, cam, 1, s);
     if (rc) return rc;
     const long long px = (long long)cam->width * cam->height;
-    dim3 grid((unsigned)((px + 255) / 256), 1);
+    dim3 grid((unsigned)((cam->width + 63) / 64), (unsigned)((cam->height + 3) / 4), 1);
     LAUNCH(KID_SHADE, s, k_shade<<<grid, 256, 0, s>>>(ctx->d_frames, to_style_dev(style), d_vis, px, (const float4*)d_pos, (const float4*)d_attr, 0, n,
                                                       id_base, owner_only, (uint32_t*)d_rgba, px));
     return PCR_OK;
