@@ -203,6 +203,11 @@ int pcr_zmerge_nccl(pcr_ctx* ctx, uint64_t* d_vis, int64_t n_px, void* comm, voi
  *   (mean xyz, min xyz, max xyz, scale) to pcr_standardize_with_stats. */
 int pcr_stats_partial(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols,
                       double* d_partial9, void* stream);
+/* Device half of C0: d_partials = [n_shards][9] doubles (every rank's pcr_stats_partial output,
+ * all-gathered in rank order), n_total = points of the whole cloud -> d_stats10, with the same
+ * roundings as a single-GPU frame.  No host synchronisation. */
+int pcr_finalize_stats(pcr_ctx* ctx, const double* d_partials, int n_shards, int64_t n_total,
+                       int in_is_f64, double* d_stats10, void* stream);
 int pcr_standardize_with_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols,
                                const float* d_radius, const float* d_rgb, const pcr_style* style,
                                const double* d_stats10, float* d_pos_out, float* d_attr_out,

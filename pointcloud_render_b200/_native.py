@@ -22,7 +22,7 @@ SYMBOLS = (
     "pcr_abi_version", "pcr_create", "pcr_destroy", "pcr_last_error", "pcr_camera_frame",
     "pcr_standardize", "pcr_render", "pcr_shade", "pcr_render_frames", "pcr_render_frames_host",
     "pcr_zmin", "pcr_zmerge_nccl", "pcr_stats_partial", "pcr_standardize_with_stats", "pcr_counters",
-    "pcr_transform_coordinates", "pcr_profile", "pcr_profile_read", "pcr_kernel_name", "pcr_set_occlusion",
+    "pcr_transform_coordinates", "pcr_profile", "pcr_profile_read", "pcr_kernel_name", "pcr_set_occlusion", "pcr_finalize_stats",
 )
 
 
@@ -84,6 +84,7 @@ def load_library():
     L.pcr_counters.argtypes = [vp, ctypes.POINTER(i64), vp]
     L.pcr_transform_coordinates.argtypes = [vp, vp, i64, i32, i32, ctypes.c_float, vp, vp]
     L.pcr_set_occlusion.argtypes = [vp, i32, i32, i64]
+    L.pcr_finalize_stats.argtypes = [vp, vp, i32, i64, i32, vp, vp]
     L.pcr_profile.argtypes = [vp, i32]
     L.pcr_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), i32]
     L.pcr_kernel_name.argtypes = [i32]
@@ -213,6 +214,15 @@ class Context:
         self._check(self.lib.pcr_stats_partial(self.handle, _ptr(pts), int(pts.dtype == torch.float64), n, cols,
                                                _ptr(out), _stream_ptr(stream)))
         return out[:9]
+
+    def finalize_stats(self, partials, n_total, is_f64=False, stream=None):
+        """partials: (k,9) float64 CUDA tensor of shard totals -> stats (10,) on the device, no host sync."""
+        import torch
+        assert partials.is_cuda and partials.dtype == torch.float64 and partials.is_contiguous()
+        out = torch.empty(10, dtype=torch.float64, device=partials.device)
+        self._check(self.lib.pcr_finalize_stats(self.handle, _ptr(partials), int(partials.numel() // 9), int(n_total), int(bool(is_f64)),
+                                                _ptr(out), _stream_ptr(stream)))
+        return out
 
     def standardize_with_stats(self, pts, style, stats10, radius=None, rgb=None, stream=None):
         import torch

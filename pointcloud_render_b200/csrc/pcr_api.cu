@@ -433,6 +433,20 @@ int pcr_stats_partial(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, 
     return PCR_OK;
 }
 
+int pcr_finalize_stats(pcr_ctx* ctx, const double* d_partials, int n_shards, int64_t n_total, int in_is_f64, double* d_stats10,
+                       void* stream)
+{
+    if (!ctx) return PCR_ERR_INVALID;
+    if (!d_partials || !d_stats10 || n_shards < 1 || n_total < 1) return fail(ctx, PCR_ERR_INVALID, "pcr_finalize_stats: NULL buffer or empty cloud");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (in_is_f64)
+        LAUNCH(KID_STATS, s, k_finalize_partials<double><<<1, 32, 0, s>>>(d_partials, n_shards, n_total, d_stats10));
+    else
+        LAUNCH(KID_STATS, s, k_finalize_partials<float><<<1, 32, 0, s>>>(d_partials, n_shards, n_total, d_stats10));
+    return PCR_OK;
+}
+
 int pcr_standardize_with_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols, const float* d_radius,
                                const float* d_rgb, const pcr_style* style, const double* d_stats10, float* d_pos_out,
                                float* d_attr_out, float* d_vel_out, void* stream)

@@ -6,8 +6,9 @@ collective anywhere; both modes are new:
   frames  — every frame is standardised and rendered independently (traj_ball_renderer.py:373),
             so a trajectory shards over ranks in contiguous blocks with NO collective.
   points  — one huge cloud is split by point range.  Two exchange steps exist:
-            C0  all-reduce of {sum xyz | min xyz | max xyz} (9 doubles) so every rank standardises
-                with the global mean / extent (example_renderer.py:96-97);
+            C0  all-gather of every shard's {sum xyz | min xyz | max xyz} (9 doubles), folded in
+                rank order and finalised on the device so every rank standardises with the same
+                global mean / extent (example_renderer.py:96-97);
             C1  min all-reduce of the packed (depth|id) z-buffer — keys are < 2^63 (the depth is a
                 positive float), so int64 MIN orders them exactly like uint64 MIN: NCCL's
                 ncclAllReduce(ncclInt64, ncclMin) over NVLink, exact and order independent.
@@ -62,6 +63,17 @@ def allreduce_stats(partial9, n_local, dtype, group=None):
     return torch.from_numpy(stats).to(partial9.device)
 
 
+def allgather_stats_device(ctx, partial9, n_total, is_f64, group=None):
+    """C0 without a host round trip: ONE all-gather of the 9 shard totals, folded in rank order and
+    finalised on the device (pcr_finalize_stats).  Every rank computes bit-identical stats."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    gathered = torch.empty((world, 9), dtype=torch.float64, device=partial9.device)
+    dist.all_gather_into_tensor(gathered, partial9.contiguous(), group=group)
+    return ctx.finalize_stats(gathered, n_total, is_f64)
+
+
 def zmerge_(vis, group=None):
     """C1.  In-place min all-reduce of the (H,W) int64 view of the uint64 keys."""
     import torch
@@ -79,13 +91,13 @@ def assemble_image_(rgba, group=None):
     return rgba
 
 
-def render_point_sharded(ctx, pts_local, id_base, cam, style, radius=None, rgb=None, group=None, shade=True):
+def render_point_sharded(ctx, pts_local, id_base, n_total, cam, style, radius=None, rgb=None, group=None, shade=True):
     """The whole point-sharded path on one rank: K0 partials -> C0 -> K1 -> K2/K3 -> C1 -> K4(owner)
-    -> byte MAX.  pts_local: (n_local, 3|6) CUDA tensor, this rank's slice of the cloud."""
+    -> byte MAX.  pts_local: (n_local, 3|6) CUDA tensor, this rank's slice of the n_total-point cloud.
+    Stream-ordered, no host synchronisation."""
     import torch
-    dtype = np.float64 if pts_local.dtype == torch.float64 else np.float32
     part = ctx.stats_partial(pts_local)
-    stats = allreduce_stats(part, pts_local.shape[0], dtype, group)
+    stats = allgather_stats_device(ctx, part, n_total, pts_local.dtype == torch.float64, group)
     pos4, attr4 = ctx.standardize_with_stats(pts_local, style, stats, radius=radius, rgb=rgb)
     vis, _ = ctx.render(pos4, attr4, cam, style, id_base=id_base, shade=False)
     zmerge_(vis, group)

@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Multi-GPU correctness check, one rank per GPU over NCCL:
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py
+
+1. frame-sharded trajectory (no collective): every rank renders its block of frames; gathered on
+   rank 0 they are byte-identical to rank 0 rendering the whole trajectory alone.
+2. point-sharded cloud (C0 all-gather of shard totals + C1 int64-min all-reduce of the z-buffer +
+   owner-only shading + byte MAX): identical to the single-GPU render, keys and image.
+Prints one JSON line on rank 0; exits non-zero on any mismatch."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from pointcloud_render_b200 import _native, sharding, synthetic  # noqa: E402
+from pointcloud_render_b200.presets import PRESETS  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    report = {"world": world}
+
+    # ---- 1. frames --------------------------------------------------------------------------
+    F, n, W, H = 4 * world + 1, 50_000, 640, 360
+    traj = synthetic.trajectory(F, n, 6, seed=3)
+    cfg = PRESETS["traj_vel"].for_trajectory(F)
+    style = cfg.style(color_mode=2)
+    cams = [cfg.camera(f, F, W, H) for f in range(F)]
+    ctx = _native.Context(device=local, max_points=n, max_w=W, max_h=H, max_batch=4)
+    a, b = sharding.frame_shard(F, rank, world)
+    mine = ctx.render_frames(torch.from_numpy(traj[a:b]).to(dev), cams[a:b], style)
+    sizes = [sharding.frame_shard(F, r, world) for r in range(world)]
+    maxlen = max(e - s for s, e in sizes)
+    pad = torch.zeros((maxlen, H, W, 4), dtype=torch.uint8, device=dev)
+    pad[: b - a] = mine
+    gathered = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, gathered, dst=0)
+    if rank == 0:
+        full = ctx.render_frames(torch.from_numpy(traj).to(dev), cams, style)
+        got = torch.cat([g[: e - s] for g, (s, e) in zip(gathered, sizes)])
+        report["frames_identical"] = bool(torch.equal(got, full))
+    ctx.close()
+
+    # ---- 2. points --------------------------------------------------------------------------
+    n, W, H = 3_000_001, 2048, 2048
+    cloud = synthetic.cloud(n, "gauss", seed=11)
+    cfg = PRESETS["example"]
+    style, cam = cfg.style(color_mode=1), cfg.camera(0, 1, W, H)
+    a, b = sharding.point_shard(n, rank, world)
+    ctx = _native.Context(device=local, max_points=n, max_w=W, max_h=H, max_batch=1)
+    vis, rgba = sharding.render_point_sharded(ctx, torch.from_numpy(cloud[a:b]).to(dev), a, n, cam, style)
+    torch.cuda.synchronize()
+    if rank == 0:
+        whole = torch.from_numpy(cloud).to(dev)
+        # same global stats as the sharded run: totals folded in rank order
+        parts = torch.stack([ctx.stats_partial(whole[s:e]) for s, e in (sharding.point_shard(n, r, world) for r in range(world))])
+        stats = ctx.finalize_stats(parts.contiguous(), n)
+        pos4, attr4 = ctx.standardize_with_stats(whole, style, stats)
+        vis1, rgba1 = ctx.render(pos4, attr4, cam, style)
+        report["points_keys_identical"] = bool(torch.equal(vis, vis1))
+        report["points_image_identical"] = bool(torch.equal(rgba, rgba1))
+        own = ctx.standardize(whole, style)[0]                       # single-GPU stats path
+        report["stats_path_max_abs_diff"] = float((own - pos4).abs().max())
+        ids = _native.keys_to_ids(vis)
+        report["sphere_pixels"] = int((ids < n).sum())
+    ctx.close()
+    dist.barrier()
+    if rank == 0:
+        print(json.dumps(report), flush=True)
+        ok = report["frames_identical"] and report["points_keys_identical"] and report["points_image_identical"]
+        dist.destroy_process_group()
+        sys.exit(0 if ok else 1)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
