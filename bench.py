@@ -41,7 +41,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="H", choices=["H", "C2", "C3", "C4"])
+    ap.add_argument("--workload", default="H", choices=["H", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--points", type=int, default=0, help="override the workload's point count (C5 scaling studies)")
     ap.add_argument("--frames-per-step", type=int, default=0, help="frames per step per GPU (0 = workload default)")
     ap.add_argument("--ring", type=int, default=0, help="resident frames per GPU (0 = enough to exceed L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -53,7 +54,7 @@ def parse_args():
 def workload_spec(name, frames_per_step):
     from pointcloud_render_b200 import synthetic
     c = dict(synthetic.CONFIGS[name])
-    default_fps = {"H": 16, "C4": 16, "C3": 32, "C2": 32}[name]
+    default_fps = {"H": 16, "C4": 16, "C3": 32, "C2": 32, "C5": 1}[name]
     c["frames_per_step"] = frames_per_step or default_fps
     b_in = 4 * c["cols"] + (4 if c["radii"] else 0)
     # input read once, u64 visibility written once, RGBA8 written once
@@ -238,12 +239,107 @@ def run_reference(args, spec, rank, world):
 
 
 # --------------------------------------------------------------------------------------------------
+def run_point_sharded(args, spec, rank, world, local_rank):
+    """C5: ONE huge cloud, point-sharded over the ranks (strong scaling): K0 partials -> C0 all-gather
+    -> K1 -> K2/K3 into a full-frame z-buffer per rank -> C1 int64-min all-reduce over NVLink ->
+    owner-only K4 -> byte-MAX all-reduce of the RGBA8 image.  A step = one frame of the cloud."""
+    import torch
+    import torch.distributed as dist
+    from pointcloud_render_b200 import _native, sharding, synthetic
+    from pointcloud_render_b200.presets import PRESETS
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n, W, H = spec["points"], spec["width"], spec["height"]
+    a, b = sharding.point_shard(n, rank, world)
+    rng = np.random.default_rng(1000 + rank)
+    local = torch.from_numpy(rng.standard_normal((b - a, 3)).astype(np.float32)).cuda()   # a Gaussian cloud, shard by shard
+    cfg = PRESETS[spec["preset"]]
+    style, cam = cfg.style(color_mode=spec["color_mode"]), cfg.camera(0, 1, W, H)
+    ctx = _native.Context(device=local_rank, max_points=b - a, max_w=W, max_h=H, max_batch=1)
+
+    def step():
+        if world > 1:
+            return sharding.render_point_sharded(ctx, local, a, n, cam, style)
+        pos4, attr4 = ctx.standardize(local, style)
+        return ctx.render(pos4, attr4, cam, style)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ctx.profile_read()
+    ctx.profile(True)
+    launches0 = ctx.counters()["launches"]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    if sampler:
+        sampler.begin()
+    barrier()
+    ev[0].record()
+    for _ in range(args.steps):
+        vis, rgba = step()
+    ev[1].record()
+    barrier()
+    if sampler:
+        sampler.end()
+        sampler.stop()
+    ms = ev[0].elapsed_time(ev[1])
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ctx.profile(False)
+    prof = ctx.profile_read()
+    counters = ctx.counters()
+    if rank == 0:
+        fps = args.steps / (ms * 1e-3)
+        kernels = {k: {"ms_total": round(v[0], 4), "launches": int(v[1]), "us_per_launch": round(v[0] / v[1] * 1e3, 3)}
+                   for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+        kernel_ms = sum(v[0] for v in prof.values())
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.isfile(peaks_path) else 6650.0
+        per_gpu_bytes = (b - a) * 12 + W * H * 8 + W * H * 4 // world       # SURVEY.md 8(d), point-sharded definition
+        top = max(prof.items(), key=lambda kv: kv[1][0])
+        line = {"metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "mpoints_per_s": fps * n / 1e6,
+                "config": {"workload": f"C5: one {n}-point Gaussian cloud at {W}x{H}, preset {spec['preset']}, point-sharded over {world} GPU(s)",
+                           "points": n, "width": W, "height": H, "points_per_gpu": b - a,
+                           "l2_policy": f"inputs larger than L2 ({(b - a) * 12 / 1e6:.0f} MB of points + {W * H * 8 / 1e6:.0f} MB z-buffer per GPU)",
+                           "parallelism": "single GPU" if world == 1 else f"points sharded over {world} GPUs; C0 all-gather (72 B/rank) + C1 "
+                                          f"ncclAllReduce(int64,min) of {W * H * 8 / 1e6:.0f} MB + byte-MAX all-reduce of {W * H * 4 / 1e6:.0f} MB RGBA8"},
+                "e2e": None, "gpu_launches": int(counters["launches"] - launches0), "kernels": kernels,
+                "kernel_ms_per_step": kernel_ms / args.steps, "collective_and_gap_ms_per_step": ms / args.steps - kernel_ms / args.steps,
+                "roofline": {"bound": "hbm", "kernel": top[0], "achieved": per_gpu_bytes / (top[1][0] / top[1][1] * 1e-3) / 1e9, "peak": peak,
+                             "unit": "GB/s", "frac": per_gpu_bytes / (top[1][0] / top[1][1] * 1e-3) / 1e9 / peak, "traffic": None,
+                             "algorithmic_bytes_per_launch": per_gpu_bytes,
+                             "note": "per-GPU algorithmic bytes = shard points*12 + W*H*8 (own z-buffer) + W*H*4/world (image slice)"},
+                "clocks": sampler.summary() if sampler else None, "pairs_last_frame": counters["pairs_last_frame"],
+                "overflow_frames": counters["overflow_frames"],
+                "sphere_pixels": int((_native.keys_to_ids(vis) < n).sum())}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     spec = workload_spec(args.workload, args.frames_per_step)
+    if args.points:
+        spec["points"] = args.points
+    if args.workload == "C5" and args.impl == "ours":
+        run_point_sharded(args, spec, rank, world, local_rank)
+        return
 
     if args.impl == "reference":
         run_reference(args, spec, rank, world)

@@ -345,7 +345,7 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     ctx->device = device; ctx->max_points = max_points; ctx->max_w = max_w; ctx->max_h = max_h; ctx->max_batch = max_batch;
     ctx->pair_cap = pair_capacity > 0 ? pair_capacity : 8 * max_points + 65536;
     if (ctx->pair_cap > 0xFFFFFFF0ll) ctx->pair_cap = 0xFFFFFFF0ll;
-    ctx->tiles_cap = ((max_w + TILE - 1) / TILE) * ((max_h + TILE - 1) / TILE);
+    ctx->tiles_cap = (((max_w + TILE - 1) / TILE) * ((max_h + TILE - 1) / TILE) + 3) & ~3;   // multiple of 4: k_scan_tiles uses uint4
     ctx->item_cap = ctx->tiles_cap + (int)(ctx->pair_cap / ITEM_SPHERES) + 1;
     ctx->hz_cap = ((max_w + HZ_W - 1) / HZ_W) * ((max_h + HZ_H - 1) / HZ_H);
     if (const char* e = getenv("PCR_OCCLUSION")) ctx->occlusion = atoi(e);
@@ -369,7 +369,7 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     ALLOC(ctx->stats, sizeof(double) * B * 10);
     ALLOC(ctx->done, sizeof(unsigned int) * B);
     ALLOC(ctx->counts, sizeof(unsigned int) * B * Tn);
-    ALLOC(ctx->offsets, sizeof(unsigned int) * B * (Tn + 1));
+    ALLOC(ctx->offsets, sizeof(unsigned int) * B * (Tn + 4));   // per-frame stride tiles_cap + 4 keeps uint4 alignment
     ALLOC(ctx->cursor, sizeof(unsigned int) * B * Tn);
     ALLOC(ctx->pairs, sizeof(unsigned int) * B * (size_t)ctx->pair_cap);
     ALLOC(ctx->overflow, sizeof(unsigned int) * B);

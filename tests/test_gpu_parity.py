@@ -392,3 +392,22 @@ def test_facade_end_to_end(tmp_path, orc):
     rgba = rb.render_trajectory(synthetic.trajectory(3, 500, 6), total_frames=3)
     assert tuple(rgba.shape) == (3, 180, 320, 4)
     renderers.release_engines()
+
+
+def test_large_film_uses_global_atomic_binning(lib, orc):
+    """4096 x 4096 (65 536 tiles — too many for the shared-memory tile histogram, so K2 takes the
+    per-pair global-atomic path) with large projected spheres, pre-pass on and off."""
+    n, W, H = 300_000, 4096, 4096
+    cfg = PRESETS["example"]
+    p = orc.transform_coordinates(orc.standardize_point_cloud(synthetic.cloud(n, "gauss", 21)), True)
+    pos4 = np.concatenate([p, np.full((n, 1), 0.01, np.float32)], axis=1)
+    want = orc.visibility(pos4, orc_frame(orc, cfg, 0, 1, W, H), orc_scene(orc, cfg))
+    c = _native.Context(device=0, max_points=n, max_w=W, max_h=H, max_batch=1)
+    try:
+        for mode in (0, 1):
+            c.set_occlusion(mode=mode)
+            vis, _ = c.render(dev(pos4), dev(np.full((n, 4), 0.3, np.float32)), cfg.camera(0, 1, W, H), cfg.style(), shade=False)
+            np.testing.assert_array_equal(keys(vis), want)
+            assert c.counters()["overflow_frames"] == 0
+    finally:
+        c.close()
