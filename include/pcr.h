@@ -96,7 +96,16 @@ typedef struct pcr_style {
     int32_t xform;       /* 0: the reference's axis transform (permute, flip, lift);
                             1: none (standardise only) — lets the facade expose
                             standardize_point_cloud / transform_coordinates separately */
+    int32_t mean_mode;   /* how the centre of standardize_point_cloud is summed (PCR_MEAN_*)      */
 } pcr_style;
+
+/* The reference's np.mean(axis=0) is a SEQUENTIAL sum in the input dtype (example_renderer.py:96),
+ * whose float32 rounding error grows with N.  PCR_MEAN_SEQUENTIAL reproduces it bit for bit (one
+ * thread per axis, ~2.4 ms per million points); PCR_MEAN_F64 sums in float64 in parallel and rounds
+ * once (order independent, more accurate, not bit-identical to numpy for float32 input);
+ * PCR_MEAN_AUTO = sequential up to PCR_MEAN_AUTO_MAX_POINTS points per frame, float64 above. */
+enum { PCR_MEAN_AUTO = 0, PCR_MEAN_SEQUENTIAL = 1, PCR_MEAN_F64 = 2 };
+#define PCR_MEAN_AUTO_MAX_POINTS 131072
 
 /* f32 camera frame derived on the HOST in double precision from a pcr_camera.
  * Kernels and the parity oracle consume exactly these numbers. */

@@ -16,6 +16,8 @@ ID_MISS = 0xFFFFFFFF
 KEY_MISS = 0x7F800000FFFFFFFF
 
 COLOR_CONST, COLOR_POSITION, COLOR_VELOCITY, COLOR_USER = 0, 1, 2, 3
+MEAN_AUTO, MEAN_SEQUENTIAL, MEAN_F64 = 0, 1, 2     # pcr_style.mean_mode
+MEAN_AUTO_MAX_POINTS = 131072
 
 # every symbol include/pcr.h declares (tests check the library exports all of them)
 SYMBOLS = (
@@ -40,7 +42,7 @@ class Style(ctypes.Structure):
                 ("has_floor", ctypes.c_int32), ("floor_z", ctypes.c_float), ("floor_min", ctypes.c_float * 2),
                 ("floor_max", ctypes.c_float * 2), ("floor_albedo", ctypes.c_float), ("light_z", ctypes.c_float),
                 ("light_half", ctypes.c_float), ("radiance", ctypes.c_float), ("bounce", ctypes.c_float),
-                ("xform", ctypes.c_int32)]
+                ("xform", ctypes.c_int32), ("mean_mode", ctypes.c_int32)]
 
 
 class Frame(ctypes.Structure):
@@ -110,7 +112,7 @@ def make_camera(origin, target, up=(0.0, 0.0, 1.0), fov_x_deg=30.0, near_clip=0.
 
 def make_style(color_mode=COLOR_CONST, const_rgb=(0.3, 0.3, 0.3), radius=0.01, flip_x=True, z_lift=0.0125,
                vel_norm=10.0, has_floor=True, floor_z=-0.2, floor_min=(-10.0, -10.0), floor_max=(10.0, 10.0),
-               floor_albedo=1.0, light_z=15.0, light_half=8.0, radiance=4.0, bounce=1.0, xform=0):
+               floor_albedo=1.0, light_z=15.0, light_half=8.0, radiance=4.0, bounce=1.0, xform=0, mean_mode=MEAN_AUTO):
     s = Style()
     s.color_mode = int(color_mode)
     s.const_rgb = (ctypes.c_float * 3)(*const_rgb)
@@ -119,7 +121,7 @@ def make_style(color_mode=COLOR_CONST, const_rgb=(0.3, 0.3, 0.3), radius=0.01, f
     s.floor_min = (ctypes.c_float * 2)(*floor_min)
     s.floor_max = (ctypes.c_float * 2)(*floor_max)
     s.floor_albedo, s.light_z, s.light_half = float(floor_albedo), float(light_z), float(light_half)
-    s.radiance, s.bounce, s.xform = float(radiance), float(bounce), int(xform)
+    s.radiance, s.bounce, s.xform, s.mean_mode = float(radiance), float(bounce), int(xform), int(mean_mode)
     return s
 
 

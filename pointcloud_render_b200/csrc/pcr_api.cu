@@ -24,10 +24,10 @@ constexpr int RING_SLOTS = 4;
 constexpr int MAX_STAT_BLOCKS = 1184;   // 148 SMs x 8
 
 enum KernelId { KID_STATS = 0, KID_TRANSFORM, KID_PROJECT, KID_SCAN, KID_SCATTER, KID_RASTER, KID_HIZ, KID_SHADE,
-                KID_ZMIN, KID_AXIS, KID_FILL, KID_COUNT };
+                KID_ZMIN, KID_AXIS, KID_FILL, KID_MEAN, KID_COUNT };
 const char* const kKernelNames[KID_COUNT] = {"k_stats", "k_transform", "k_project_count", "k_scan_tiles", "k_scatter",
                                              "k_raster_tiles", "k_hiz", "k_shade", "k_zmin", "k_axis_transform",
-                                             "k_fill_tiles"};
+                                             "k_fill_tiles", "k_mean_sequential"};
 constexpr size_t PROF_MAX_RECORDS = 1 << 16;
 
 struct ProfRec { int kid; cudaEvent_t a, b; };
@@ -216,7 +216,7 @@ int upload_frames(pcr_ctx* ctx, const pcr_camera* cams, int nb, cudaStream_t str
 }
 
 int launch_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, long long n, int cols, long long frame_stride,
-                 int nb, double* partials, double* stats, int finalize, cudaStream_t stream)
+                 int nb, double* partials, double* stats, int finalize, cudaStream_t stream, int mean_mode = PCR_MEAN_F64)
 {
     int blocks = (int)std::min<long long>((n + 256 * 8 - 1) / (256 * 8), MAX_STAT_BLOCKS);
     blocks = std::max(blocks, 1);
@@ -227,6 +227,14 @@ int launch_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, long long n, int
         LAUNCH(KID_STATS, stream, k_stats<double><<<grid, 256, 0, stream>>>((const double*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, ctx->done, finalize, 0));
     else
         LAUNCH(KID_STATS, stream, k_stats<float><<<grid, 256, 0, stream>>>((const float*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, ctx->done, finalize, vec));
+    // the reference's own (sequential, input-dtype) mean replaces the f64 one when asked for
+    const bool sequential = finalize == 1 && (mean_mode == PCR_MEAN_SEQUENTIAL || (mean_mode == PCR_MEAN_AUTO && n <= PCR_MEAN_AUTO_MAX_POINTS));
+    if (sequential) {
+        if (in_is_f64)
+            LAUNCH(KID_MEAN, stream, k_mean_sequential<double><<<nb, 128, 0, stream>>>((const double*)d_in, n, cols, frame_stride, stats));
+        else
+            LAUNCH(KID_MEAN, stream, k_mean_sequential<float><<<nb, 128, 0, stream>>>((const float*)d_in, n, cols, frame_stride, stats));
+    }
     return PCR_OK;
 }
 
@@ -313,6 +321,7 @@ int check_common(pcr_ctx* ctx, long long n, int cols, const pcr_style* style)
     if (!ctx) return PCR_ERR_INVALID;
     if (!style) return fail(ctx, PCR_ERR_INVALID, "style is NULL");
     if (n < 0 || (cols != 3 && cols != 6)) return fail(ctx, PCR_ERR_INVALID, "n < 0 or cols not 3|6");
+    if (style->mean_mode < 0 || style->mean_mode > 2) return fail(ctx, PCR_ERR_INVALID, "mean_mode not in {0,1,2}");
     if (n > ctx->max_points) return fail(ctx, PCR_ERR_CAPACITY, "n exceeds the context's max_points");
     return PCR_OK;
 }
@@ -469,7 +478,7 @@ int pcr_standardize(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, in
     if (!d_in || !d_pos_out || !d_attr_out) return fail(ctx, PCR_ERR_INVALID, "pcr_standardize: NULL buffer");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
-    rc = launch_stats(ctx, d_in, in_is_f64, n, cols, 0, 1, ctx->partials, ctx->stats, 1, s);
+    rc = launch_stats(ctx, d_in, in_is_f64, n, cols, 0, 1, ctx->partials, ctx->stats, 1, s, style->mean_mode);
     if (rc) return rc;
     rc = launch_transform(ctx, d_in, in_is_f64, n, cols, 0, 1, d_radius, d_rgb, ctx->stats, to_style_dev(style),
                           (float4*)d_pos_out, (float4*)d_attr_out, (float4*)d_vel_out, 0, s);
@@ -547,7 +556,7 @@ int pcr_render_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, 
         rc = upload_frames(ctx, cams + f0, nb, s);
         if (rc) return rc;
         const char* in = (const char*)d_in + (size_t)f0 * frame_stride * elem;
-        rc = launch_stats(ctx, in, in_is_f64, n, cols, frame_stride, nb, ctx->partials, ctx->stats, 1, s);
+        rc = launch_stats(ctx, in, in_is_f64, n, cols, frame_stride, nb, ctx->partials, ctx->stats, 1, s, style->mean_mode);
         if (rc) return rc;
         rc = launch_transform(ctx, in, in_is_f64, n, cols, frame_stride, nb, d_radius, d_rgb, ctx->stats, st, ctx->pos, ctx->attr,
                               nullptr, ctx->max_points, s);

@@ -65,12 +65,12 @@ class RenderConfig:
         return _native.make_camera(self.camera_position(frame_index, total_frames), self.target, self.up, self.fov,
                                    self.near_clip, self.far_clip, width or self.width, height or self.height)
 
-    def style(self, color_mode=_native.COLOR_CONST, xform=0):
+    def style(self, color_mode=_native.COLOR_CONST, xform=0, mean_mode=_native.MEAN_AUTO):
         return _native.make_style(color_mode=color_mode, const_rgb=self.const_rgb, radius=self.radius,
                                   flip_x=self.flip_x, z_lift=self.z_lift, vel_norm=self.vel_norm, has_floor=True,
                                   floor_z=self.floor_z, floor_min=self.floor_min, floor_max=self.floor_max,
                                   floor_albedo=self.floor_albedo, light_z=self.light_z, light_half=self.light_half,
-                                  radiance=self.radiance, bounce=self.bounce, xform=xform)
+                                  radiance=self.radiance, bounce=self.bounce, xform=xform, mean_mode=mean_mode)
 
     def for_trajectory(self, n_frames):
         """Stretch the 220-frame schedule (199 motion + 20 fade) over an n_frames trajectory
