@@ -362,7 +362,7 @@ def main():
     resident = host.cuda(non_blocking=True)
     radius_np = synthetic.radii(n) if spec["radii"] else None
     radius = torch.from_numpy(radius_np).cuda() if radius_np is not None else None
-    ctx = _native.Context(device=local_rank, max_points=n, max_w=W, max_h=H, max_batch=min(B, 8))
+    ctx = _native.Context(device=local_rank, max_points=n, max_w=W, max_h=H, max_batch=min(B, 16))
     cams_all, cfg = cameras_for(spec, rank * 1000, ring)
     style = cfg.style(color_mode=spec["color_mode"])
     rgba = torch.empty((B, H, W, 4), dtype=torch.uint8, device="cuda")

@@ -24,10 +24,10 @@ constexpr int RING_SLOTS = 4;
 constexpr int MAX_STAT_BLOCKS = 1184;   // 148 SMs x 8
 
 enum KernelId { KID_STATS = 0, KID_TRANSFORM, KID_PROJECT, KID_SCAN, KID_SCATTER, KID_RASTER, KID_HIZ, KID_SHADE,
-                KID_ZMIN, KID_AXIS, KID_FILL, KID_MEAN, KID_COUNT };
+                KID_ZMIN, KID_AXIS, KID_FILL, KID_MEAN, KID_LUT, KID_COUNT };
 const char* const kKernelNames[KID_COUNT] = {"k_stats", "k_transform", "k_project_count", "k_scan_tiles", "k_scatter",
                                              "k_raster_tiles", "k_hiz", "k_shade", "k_zmin", "k_axis_transform",
-                                             "k_fill_tiles", "k_mean_sequential"};
+                                             "k_fill_tiles", "k_mean_sequential", "k_build_floor_lut"};
 constexpr size_t PROF_MAX_RECORDS = 1 << 16;
 
 struct ProfRec { int kid; cudaEvent_t a, b; };
@@ -55,6 +55,9 @@ struct pcr_ctx {
     uint2* items = nullptr;
     int item_cap = 0;
     int smem_optin = 48 * 1024;       // max dynamic shared memory per block (opt-in)
+    float* lut = nullptr;             // floor form-factor table (LUT_N^2), rebuilt when the scene constants change
+    float lut_key[7] = {0, 0, 0, 0, 0, 0, 0};
+    bool lut_valid = false;
     unsigned int* hz = nullptr;       // [max_batch][hz_cap] farthest pre-pass depth per 8x4 pixel block
     int hz_cap = 0;
     int occlusion = -1;               // -1 auto (n >= occlusion_min_points), 0 off, 1 always
@@ -196,6 +199,26 @@ BinDev bin_of(pcr_ctx* c)
     return b;
 }
 
+// Floor form-factor table for this style (built once per distinct set of scene constants).
+int floor_lut(pcr_ctx* ctx, const StyleDev& st, cudaStream_t stream, FloorLut* out)
+{
+    out->data = nullptr; out->x0 = out->y0 = out->inv_cx = out->inv_cy = 0.0f;
+    const float w = st.floor_max[0] - st.floor_min[0], h = st.floor_max[1] - st.floor_min[1];
+    if (!st.has_floor || !(st.light_z > st.floor_z) || !(w > 0.0f) || !(h > 0.0f)) return PCR_OK;     // evaluated directly
+    const float key[7] = {st.floor_z, st.floor_min[0], st.floor_min[1], st.floor_max[0], st.floor_max[1], st.light_z, st.light_half};
+    const float cx = w / (float)(LUT_N - 1), cy = h / (float)(LUT_N - 1);
+    if (!ctx->lut) CK(cudaMalloc((void**)&ctx->lut, sizeof(float) * LUT_N * LUT_N));
+    if (!ctx->lut_valid || memcmp(key, ctx->lut_key, sizeof(key)) != 0) {
+        dim3 grid((LUT_N + 255) / 256, LUT_N);
+        LAUNCH(KID_LUT, stream, k_build_floor_lut<<<grid, 256, 0, stream>>>(ctx->lut, st.floor_min[0], st.floor_min[1], cx, cy,
+                                                                            st.light_z - st.floor_z, st.light_half));
+        memcpy(ctx->lut_key, key, sizeof(key));
+        ctx->lut_valid = true;
+    }
+    out->data = ctx->lut; out->x0 = st.floor_min[0]; out->y0 = st.floor_min[1]; out->inv_cx = 1.0f / cx; out->inv_cy = 1.0f / cy;
+    return PCR_OK;
+}
+
 // Upload `nb` cameras into d_frames through the pinned ring.
 int upload_frames(pcr_ctx* ctx, const pcr_camera* cams, int nb, cudaStream_t stream)
 {
@@ -309,8 +332,11 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         if (rc) return rc;
     }
     if (rgba) {
+        FloorLut lut;
+        int rc = floor_lut(ctx, st, stream, &lut);
+        if (rc) return rc;
         dim3 grid((unsigned)((W + 63) / 64), (unsigned)((H + 3) / 4), nb);
-        LAUNCH(KID_SHADE, stream, k_shade<<<grid, 256, 0, stream>>>(ctx->d_frames, st, vis, vis_stride, pos, attr, in_stride, n, id_base, owner_only,
+        LAUNCH(KID_SHADE, stream, k_shade<<<grid, 256, 0, stream>>>(ctx->d_frames, st, lut, vis, vis_stride, pos, attr, in_stride, n, id_base, owner_only,
                                                                     (uint32_t*)rgba, rgba_stride));
     }
     return PCR_OK;
@@ -412,7 +438,7 @@ void pcr_destroy(pcr_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     void* frees[] = {ctx->pos, ctx->attr, ctx->sph, ctx->rect, ctx->partials, ctx->stats, ctx->done, ctx->counts, ctx->offsets,
-                     ctx->cursor, ctx->pairs, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
+                     ctx->cursor, ctx->pairs, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
                      ctx->stage_rgba[0], ctx->stage_rgba[1], ctx->stage_vis[0], ctx->stage_vis[1], ctx->stage_radius, ctx->stage_rgb};
     for (void* p : frees) if (p) cudaFree(p);
     if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
@@ -528,7 +554,10 @@ int pcr_shade(pcr_ctx* ctx, const uint64_t* d_vis, const float* d_pos, const flo
     if (rc) return rc;
     const long long px = (long long)cam->width * cam->height;
     dim3 grid((unsigned)((cam->width + 63) / 64), (unsigned)((cam->height + 3) / 4), 1);
-    LAUNCH(KID_SHADE, s, k_shade<<<grid, 256, 0, s>>>(ctx->d_frames, to_style_dev(style), d_vis, px, (const float4*)d_pos, (const float4*)d_attr, 0, n,
+    FloorLut lut;
+    rc = floor_lut(ctx, to_style_dev(style), s, &lut);
+    if (rc) return rc;
+    LAUNCH(KID_SHADE, s, k_shade<<<grid, 256, 0, s>>>(ctx->d_frames, to_style_dev(style), lut, d_vis, px, (const float4*)d_pos, (const float4*)d_attr, 0, n,
                                                       id_base, owner_only, (uint32_t*)d_rgba, px));
     return PCR_OK;
 }
