@@ -38,7 +38,7 @@ import numpy as np  # noqa: E402
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="H", choices=["H", "C2", "C3", "C4", "C5"])
@@ -102,7 +102,7 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.samples, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -409,8 +409,6 @@ def main():
         step_device(args.warmup + s)
     ev1.record()
     barrier()
-    if sampler:
-        sampler.end()
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
     ctx.profile(False)
     prof = ctx.profile_read()
@@ -435,6 +433,7 @@ def main():
                "d2h_bytes_per_step": int(B * W * H * 4), "ms_per_step": e2e_s / args.steps * 1e3,
                "api": "pcr_render_frames_host (pinned host trajectory in, pinned host RGBA8 out; copies overlap kernels)"}
     if sampler:
+        sampler.end()           # the clock record covers both timed regions (device-resident and end-to-end)
         sampler.stop()
 
     if rank != 0:
@@ -463,8 +462,9 @@ def main():
         achieved = bytes_per_launch / (top_ms / top_cnt * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.isfile(tpath):
-            traffic = json.load(open(tpath)).get(args.workload, {}).get(top[0])
+        if os.path.isfile(tpath):              # dram__bytes_read+write per frame of one launch, from the committed ncu capture
+            per_frame = json.load(open(tpath)).get(args.workload, {}).get(top[0], {}).get("dram_bytes_per_frame_per_launch")
+            traffic = per_frame * frames_per_launch if per_frame else None
         roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": bytes_per_launch, "frames_per_launch": frames_per_launch,

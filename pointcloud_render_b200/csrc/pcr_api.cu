@@ -274,7 +274,41 @@ int launch_transform(pcr_ctx* ctx, const void* d_in, int in_is_f64, long long n,
 }
 
 // K2a -> scan -> K2b -> K3 (-> fallback) (-> K4) for nb frames whose cameras are already in d_frames.
-int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long in_stride, long long n, int nb,
+// Type-erased raw source of the fused path (pcr_render_frames): K1 is evaluated inside K2a / K4.
+struct RawSrc {
+    const void* in; int is_f64; long long frame_stride; int cols; const double* stats; const float* radius; const float* rgb;
+};
+
+template <typename T>
+RawFrames<T> raw_frames(const RawSrc* r)
+{
+    RawFrames<T> f;
+    f.in = r ? (const T*)r->in : nullptr; f.frame_stride = r ? r->frame_stride : 0; f.cols = r ? r->cols : 3;
+    f.stats = r ? r->stats : nullptr; f.radius = r ? r->radius : nullptr; f.user_rgb = r ? r->rgb : nullptr;
+    return f;
+}
+
+int launch_shade(pcr_ctx* ctx, const StyleDev& st, const uint64_t* vis, long long vis_stride, const float4* pos, const float4* attr,
+                 long long in_stride, const RawSrc* raw, long long n, int nb, uint32_t id_base, int owner_only, int W, int H,
+                 uint8_t* rgba, long long rgba_stride, cudaStream_t stream)
+{
+    FloorLut lut;
+    int rc = floor_lut(ctx, st, stream, &lut);
+    if (rc) return rc;
+    dim3 grid((unsigned)((W + 63) / 64), (unsigned)((H + 3) / 4), nb);
+    if (!raw)
+        LAUNCH(KID_SHADE, stream, k_shade<float, false><<<grid, 256, 0, stream>>>(ctx->d_frames, st, lut, vis, vis_stride, pos, attr, in_stride,
+                                                                                 raw_frames<float>(nullptr), n, id_base, owner_only, (uint32_t*)rgba, rgba_stride));
+    else if (raw->is_f64)
+        LAUNCH(KID_SHADE, stream, k_shade<double, true><<<grid, 256, 0, stream>>>(ctx->d_frames, st, lut, vis, vis_stride, nullptr, nullptr, 0,
+                                                                                 raw_frames<double>(raw), n, id_base, owner_only, (uint32_t*)rgba, rgba_stride));
+    else
+        LAUNCH(KID_SHADE, stream, k_shade<float, true><<<grid, 256, 0, stream>>>(ctx->d_frames, st, lut, vis, vis_stride, nullptr, nullptr, 0,
+                                                                                raw_frames<float>(raw), n, id_base, owner_only, (uint32_t*)rgba, rgba_stride));
+    return PCR_OK;
+}
+
+int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long in_stride, const RawSrc* raw, long long n, int nb,
                   uint32_t id_base, const StyleDev& st, int W, int H, uint64_t* vis, long long vis_stride,
                   uint8_t* rgba, long long rgba_stride, int owner_only, cudaStream_t stream)
 {
@@ -293,8 +327,16 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         if (!use_smem) gx = (unsigned)std::max<long long>(1, (np + BIN_THREADS * 4 - 1) / (BIN_THREADS * 4));
         if (np > 0) {
             dim3 grid(gx, nb);
-            LAUNCH(KID_PROJECT, stream, k_project_count<<<grid, BIN_THREADS, use_smem ? tiles * 4 : 0, stream>>>(
-                pos, np, in_stride, step, ctx->d_frames, ctx->sph, ctx->rect, ctx->max_points, bin, use_smem, hz, ctx->hz_cap));
+            const size_t sm = use_smem ? (size_t)tiles * 4 : 0;
+            if (!raw)
+                LAUNCH(KID_PROJECT, stream, (k_project_count<float, false><<<grid, BIN_THREADS, sm, stream>>>(
+                    pos, np, in_stride, raw_frames<float>(nullptr), st, step, ctx->d_frames, ctx->sph, ctx->rect, ctx->max_points, bin, use_smem, hz, ctx->hz_cap)));
+            else if (raw->is_f64)
+                LAUNCH(KID_PROJECT, stream, (k_project_count<double, true><<<grid, BIN_THREADS, sm, stream>>>(
+                    nullptr, np, 0, raw_frames<double>(raw), st, step, ctx->d_frames, ctx->sph, ctx->rect, ctx->max_points, bin, use_smem, hz, ctx->hz_cap)));
+            else
+                LAUNCH(KID_PROJECT, stream, (k_project_count<float, true><<<grid, BIN_THREADS, sm, stream>>>(
+                    nullptr, np, 0, raw_frames<float>(raw), st, step, ctx->d_frames, ctx->sph, ctx->rect, ctx->max_points, bin, use_smem, hz, ctx->hz_cap)));
         }
         LAUNCH(KID_SCAN, stream, k_scan_tiles<<<nb, 1024, 0, stream>>>(ctx->d_frames, bin, np));
         if (np > 0) {
@@ -331,14 +373,7 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         int rc = pass(n, 1, nullptr, 0);
         if (rc) return rc;
     }
-    if (rgba) {
-        FloorLut lut;
-        int rc = floor_lut(ctx, st, stream, &lut);
-        if (rc) return rc;
-        dim3 grid((unsigned)((W + 63) / 64), (unsigned)((H + 3) / 4), nb);
-        LAUNCH(KID_SHADE, stream, k_shade<<<grid, 256, 0, stream>>>(ctx->d_frames, st, lut, vis, vis_stride, pos, attr, in_stride, n, id_base, owner_only,
-                                                                    (uint32_t*)rgba, rgba_stride));
-    }
+    if (rgba) return launch_shade(ctx, st, vis, vis_stride, pos, attr, in_stride, raw, n, nb, id_base, owner_only, W, H, rgba, rgba_stride, stream);
     return PCR_OK;
 }
 
@@ -392,12 +427,12 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     if (e == cudaSuccess) {
         ctx->num_sms = prop.multiProcessorCount;
         ctx->smem_optin = (int)std::min<size_t>(prop.sharedMemPerBlockOptin, 200 * 1024);
-        e = cudaFuncSetAttribute(k_project_count, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+        e = cudaFuncSetAttribute(k_project_count<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
     }
 #define ALLOC(ptr, bytes) if (e == cudaSuccess) e = cudaMalloc((void**)&(ptr), (bytes))
-    ALLOC(ctx->pos, sizeof(float4) * B * N);
-    ALLOC(ctx->attr, sizeof(float4) * B * N);
     ALLOC(ctx->sph, sizeof(float4) * B * N);
     ALLOC(ctx->rect, sizeof(ushort4) * B * N);
     ALLOC(ctx->partials, sizeof(double) * B * MAX_STAT_BLOCKS * 9);
@@ -538,7 +573,7 @@ int pcr_render(pcr_ctx* ctx, const float* d_pos, const float* d_attr, int64_t n,
     rc = upload_frames(ctx, cam, 1, s);
     if (rc) return rc;
     const long long px = (long long)cam->width * cam->height;
-    return launch_render(ctx, (const float4*)d_pos, (const float4*)d_attr, 0, n, 1, id_base, to_style_dev(style), cam->width,
+    return launch_render(ctx, (const float4*)d_pos, (const float4*)d_attr, 0, nullptr, n, 1, id_base, to_style_dev(style), cam->width,
                          cam->height, d_vis, px, d_rgba, px, 0, s);
 }
 
@@ -553,12 +588,9 @@ int pcr_shade(pcr_ctx* ctx, const uint64_t* d_vis, const float* d_pos, const flo
     rc = upload_frames(ctx, cam, 1, s);
     if (rc) return rc;
     const long long px = (long long)cam->width * cam->height;
-    dim3 grid((unsigned)((cam->width + 63) / 64), (unsigned)((cam->height + 3) / 4), 1);
-    FloorLut lut;
-    rc = floor_lut(ctx, to_style_dev(style), s, &lut);
+    rc = launch_shade(ctx, to_style_dev(style), d_vis, px, (const float4*)d_pos, (const float4*)d_attr, 0, nullptr, n, 1, id_base, owner_only,
+                      cam->width, cam->height, d_rgba, px, s);
     if (rc) return rc;
-    LAUNCH(KID_SHADE, s, k_shade<<<grid, 256, 0, s>>>(ctx->d_frames, to_style_dev(style), lut, d_vis, px, (const float4*)d_pos, (const float4*)d_attr, 0, n,
-                                                      id_base, owner_only, (uint32_t*)d_rgba, px));
     return PCR_OK;
 }
 
@@ -587,12 +619,11 @@ int pcr_render_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, 
         const char* in = (const char*)d_in + (size_t)f0 * frame_stride * elem;
         rc = launch_stats(ctx, in, in_is_f64, n, cols, frame_stride, nb, ctx->partials, ctx->stats, 1, s, style->mean_mode);
         if (rc) return rc;
-        rc = launch_transform(ctx, in, in_is_f64, n, cols, frame_stride, nb, d_radius, d_rgb, ctx->stats, st, ctx->pos, ctx->attr,
-                              nullptr, ctx->max_points, s);
-        if (rc) return rc;
+        // no K1 launch: K2a and K4 evaluate standardise/transform/colour from the raw frames on the fly
+        const RawSrc raw = {in, in_is_f64, frame_stride, cols, ctx->stats, d_radius, d_rgb};
         uint64_t* vis = d_vis ? d_vis + (size_t)f0 * px : ctx->vis;
         const long long vis_stride = d_vis ? px : (long long)ctx->max_w * ctx->max_h;
-        rc = launch_render(ctx, ctx->pos, ctx->attr, ctx->max_points, n, nb, 0u, st, W, H, vis, vis_stride,
+        rc = launch_render(ctx, nullptr, nullptr, 0, &raw, n, nb, 0u, st, W, H, vis, vis_stride,
                            d_rgba + (size_t)f0 * px * 4, px, 0, s);
         if (rc) return rc;
     }
