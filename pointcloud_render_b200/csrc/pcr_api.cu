@@ -45,8 +45,10 @@ struct pcr_ctx {
     long long launches = 0;
 
     // scratch, all [max_batch][...]
-    float4 *pos = nullptr, *attr = nullptr, *sph = nullptr;
-    ushort4* rect = nullptr;
+    float4* sph = nullptr;            // per survivor: camera-space sphere (cx, cy, cz, r)
+    uint4* rect = nullptr;            // per survivor: pixel bbox + sphere index (K2a -> K2b, K3)
+    unsigned int* surv_count = nullptr;
+    int gx_cap = 0;
     double *partials = nullptr, *stats = nullptr;
     unsigned int* done = nullptr;
     unsigned int *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *pairs = nullptr, *overflow = nullptr;
@@ -196,6 +198,7 @@ BinDev bin_of(pcr_ctx* c)
     b.counts = c->counts; b.offsets = c->offsets; b.cursor = c->cursor; b.pairs = c->pairs;
     b.overflow = c->overflow; b.stat_pairs = c->stat_pairs; b.tiles_cap = c->tiles_cap; b.pair_cap = c->pair_cap;
     b.item_count = c->item_count; b.item_next = c->item_next; b.items = c->items; b.item_cap = c->item_cap;
+    b.surv_count = c->surv_count; b.gx_cap = c->gx_cap;
     return b;
 }
 
@@ -325,6 +328,7 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
     auto pass = [&](long long np, int step, const unsigned int* hz, int seeded) -> int {
         unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((np + 2047) / 2048, std::max(1, 2 * resident / nb)));
         if (!use_smem) gx = (unsigned)std::max<long long>(1, (np + BIN_THREADS * 4 - 1) / (BIN_THREADS * 4));
+        gx = std::min<unsigned>(gx, (unsigned)ctx->gx_cap);
         if (np > 0) {
             dim3 grid(gx, nb);
             const size_t sm = use_smem ? (size_t)tiles * 4 : 0;
@@ -353,7 +357,7 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
             // persistent raster: CTAs pull (tile, <= ITEM_SPHERES spheres) items from per-frame queues
             dim3 grid((unsigned)std::max(1, std::min(raster_ctas, tiles * nb)));
             LAUNCH(KID_RASTER, stream, k_raster_tiles<<<grid, RASTER_THREADS, 0, stream>>>(
-                ctx->d_frames, st, ctx->sph, ctx->rect, ctx->max_points, bin, id_base, (uint32_t)step, v, vis_stride, nb, np, seeded));
+                ctx->d_frames, st, ctx->sph, ctx->rect, ctx->max_points, bin, id_base, (uint32_t)step, v, vis_stride, nb, np, seeded, (int)gx));
         }
         return PCR_OK;
     };
@@ -434,7 +438,9 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     }
 #define ALLOC(ptr, bytes) if (e == cudaSuccess) e = cudaMalloc((void**)&(ptr), (bytes))
     ALLOC(ctx->sph, sizeof(float4) * B * N);
-    ALLOC(ctx->rect, sizeof(ushort4) * B * N);
+    ALLOC(ctx->rect, sizeof(uint4) * B * N);
+    ctx->gx_cap = (int)std::max<long long>(2 * ctx->num_sms * (2048 / BIN_THREADS), (max_points + BIN_THREADS * 4 - 1) / (BIN_THREADS * 4)) + 1;
+    ALLOC(ctx->surv_count, sizeof(unsigned int) * B * (size_t)ctx->gx_cap);
     ALLOC(ctx->partials, sizeof(double) * B * MAX_STAT_BLOCKS * 9);
     ALLOC(ctx->stats, sizeof(double) * B * 10);
     ALLOC(ctx->done, sizeof(unsigned int) * B);
@@ -472,7 +478,7 @@ void pcr_destroy(pcr_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    void* frees[] = {ctx->pos, ctx->attr, ctx->sph, ctx->rect, ctx->partials, ctx->stats, ctx->done, ctx->counts, ctx->offsets,
+    void* frees[] = {ctx->surv_count, ctx->sph, ctx->rect, ctx->partials, ctx->stats, ctx->done, ctx->counts, ctx->offsets,
                      ctx->cursor, ctx->pairs, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
                      ctx->stage_rgba[0], ctx->stage_rgba[1], ctx->stage_vis[0], ctx->stage_vis[1], ctx->stage_radius, ctx->stage_rgb};
     for (void* p : frees) if (p) cudaFree(p);
