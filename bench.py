@@ -54,7 +54,7 @@ def parse_args():
 def workload_spec(name, frames_per_step):
     from pointcloud_render_b200 import synthetic
     c = dict(synthetic.CONFIGS[name])
-    default_fps = {"H": 16, "C4": 16, "C3": 32, "C2": 32, "C5": 1}[name]
+    default_fps = {"H": 16, "C4": 64, "C3": 64, "C2": 64, "C5": 1}[name]
     c["frames_per_step"] = frames_per_step or default_fps
     b_in = 4 * c["cols"] + (4 if c["radii"] else 0)
     # input read once, u64 visibility written once, RGBA8 written once

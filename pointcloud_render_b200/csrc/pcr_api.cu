@@ -83,6 +83,10 @@ struct pcr_ctx {
 
     long long last_overflow_frames = 0;
 
+    // stats-ahead pipeline of pcr_render_frames: K0 of batch k+1 runs on s_aux while batch k renders
+    cudaStream_t s_aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_stats[2] = {}, ev_free[2] = {};
+
     // per-kernel CUDA-event timing (pcr_profile / pcr_profile_read)
     bool profiling = false;
     std::vector<ProfRec> prof;
@@ -442,7 +446,7 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     ctx->gx_cap = (int)std::max<long long>(2 * ctx->num_sms * (2048 / BIN_THREADS), (max_points + BIN_THREADS * 4 - 1) / (BIN_THREADS * 4)) + 1;
     ALLOC(ctx->surv_count, sizeof(unsigned int) * B * (size_t)ctx->gx_cap);
     ALLOC(ctx->partials, sizeof(double) * B * MAX_STAT_BLOCKS * 9);
-    ALLOC(ctx->stats, sizeof(double) * B * 10);
+    ALLOC(ctx->stats, sizeof(double) * B * 10 * 2);      // double-buffered (stats-ahead pipeline)
     ALLOC(ctx->done, sizeof(unsigned int) * B);
     ALLOC(ctx->counts, sizeof(unsigned int) * B * Tn);
     ALLOC(ctx->offsets, sizeof(unsigned int) * B * (Tn + 4));   // per-frame stride tiles_cap + 4 keeps uint4 alignment
@@ -491,6 +495,9 @@ void pcr_destroy(pcr_ctx* ctx)
     }
     for (ProfRec& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
+    if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (int k = 0; k < 2; ++k) { if (ctx->ev_stats[k]) cudaEventDestroy(ctx->ev_stats[k]); if (ctx->ev_free[k]) cudaEventDestroy(ctx->ev_free[k]); }
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
@@ -618,20 +625,62 @@ int pcr_render_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, 
     const size_t elem = in_is_f64 ? 8 : 4;
     const long long frame_stride = n * cols;
     if (!d_vis) { rc = ensure_vis(ctx); if (rc) return rc; }
-    for (int f0 = 0; f0 < n_frames; f0 += ctx->max_batch) {
-        const int nb = std::min(ctx->max_batch, n_frames - f0);
+    const int B = ctx->max_batch;
+    const int nbatches = (n_frames + B - 1) / B;
+    // K0 (and the serial reference-exact mean, when selected) of batch k+1 runs on a second stream
+    // while batch k renders; the stats array is double-buffered.  The serial mean is pure latency
+    // (one warp per frame), so it hides completely behind a full batch of render kernels.
+    const bool ahead = nbatches > 1;
+    if (ahead && !ctx->s_aux) {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&ctx->s_aux, cudaStreamNonBlocking, hi));
+        CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        for (int k = 0; k < 2; ++k) {
+            CK(cudaEventCreateWithFlags(&ctx->ev_stats[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_free[k], cudaEventDisableTiming));
+        }
+    }
+    auto stats_of = [&](int k, cudaStream_t q) -> int {
+        const int f0 = k * B, nb = std::min(B, n_frames - f0);
+        const char* in = (const char*)d_in + (size_t)f0 * frame_stride * elem;
+        return launch_stats(ctx, in, in_is_f64, n, cols, frame_stride, nb, ctx->partials, ctx->stats + (size_t)(k & 1) * B * 10, 1, q,
+                            style->mean_mode);
+    };
+    if (ahead) {
+        CK(cudaEventRecord(ctx->ev_fork, s));                       // the input may still be in flight on the caller's stream
+        CK(cudaStreamWaitEvent(ctx->s_aux, ctx->ev_fork, 0));
+        rc = stats_of(0, ctx->s_aux);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev_stats[0], ctx->s_aux));
+    }
+    for (int k = 0; k < nbatches; ++k) {
+        const int f0 = k * B;
+        const int nb = std::min(B, n_frames - f0);
         rc = upload_frames(ctx, cams + f0, nb, s);
         if (rc) return rc;
         const char* in = (const char*)d_in + (size_t)f0 * frame_stride * elem;
-        rc = launch_stats(ctx, in, in_is_f64, n, cols, frame_stride, nb, ctx->partials, ctx->stats, 1, s, style->mean_mode);
-        if (rc) return rc;
+        double* stats = ctx->stats + (size_t)(k & 1) * B * 10;
+        if (ahead) {
+            CK(cudaStreamWaitEvent(s, ctx->ev_stats[k & 1], 0));
+            if (k + 1 < nbatches) {
+                if (k >= 1) CK(cudaStreamWaitEvent(ctx->s_aux, ctx->ev_free[(k + 1) & 1], 0));   // batch k-1 has released that buffer
+                rc = stats_of(k + 1, ctx->s_aux);
+                if (rc) return rc;
+                CK(cudaEventRecord(ctx->ev_stats[(k + 1) & 1], ctx->s_aux));
+            }
+        } else {
+            rc = stats_of(k, s);
+            if (rc) return rc;
+        }
         // no K1 launch: K2a and K4 evaluate standardise/transform/colour from the raw frames on the fly
-        const RawSrc raw = {in, in_is_f64, frame_stride, cols, ctx->stats, d_radius, d_rgb};
+        const RawSrc raw = {in, in_is_f64, frame_stride, cols, stats, d_radius, d_rgb};
         uint64_t* vis = d_vis ? d_vis + (size_t)f0 * px : ctx->vis;
         const long long vis_stride = d_vis ? px : (long long)ctx->max_w * ctx->max_h;
         rc = launch_render(ctx, nullptr, nullptr, 0, &raw, n, nb, 0u, st, W, H, vis, vis_stride,
                            d_rgba + (size_t)f0 * px * 4, px, 0, s);
         if (rc) return rc;
+        if (ahead) CK(cudaEventRecord(ctx->ev_free[k & 1], s));
     }
     return PCR_OK;
 }
