@@ -8,6 +8,7 @@ this package is the host-side mirror of the reference's renderer classes.  No CP
 from . import _native, presets, synthetic  # noqa: F401
 from ._native import (COLOR_CONST, COLOR_POSITION, COLOR_USER, COLOR_VELOCITY, ID_FLOOR, ID_MISS, KEY_MISS,  # noqa: F401
                       Context, load_library, make_camera, make_style)
+from .output import AsyncImageWriter, trajectory_frame_name  # noqa: F401
 from .presets import PRESETS, RenderConfig  # noqa: F401
 from .renderers import (FixedFrame199Renderer, PointCloudRenderer, RenderedScene, TrajB0Renderer, TrajB1Renderer,  # noqa: F401
                         TrajectoryBallRenderer, TrajectoryRenderer, TrajectoryVelRenderer, release_engines)

@@ -199,8 +199,12 @@ class PointCloudRenderer:
         return RenderedScene(rgba, vis)
 
     @staticmethod
-    def save_scene(output_file_path, rendered_scene):
-        """example_renderer.py:159-161: the sRGB transfer already happened in K4; this is the PNG."""
+    def save_scene(output_file_path, rendered_scene, writer=None):
+        """example_renderer.py:159-161: the sRGB transfer already happened in K4; this is the PNG.
+        With an output.AsyncImageWriter the file is written in the background, like Mitsuba's
+        write_bitmap(write_async=True); call writer.drain() before reading it back."""
+        if writer is not None:
+            return writer.submit(output_file_path, rendered_scene.numpy())
         write_png(f'{output_file_path}.png', rendered_scene.numpy())
 
     def _output_path(self, output_filename):
@@ -258,7 +262,7 @@ class TrajectoryBallRenderer(PointCloudRenderer):
         print('Done!')
 
     # ---- batched trajectory path: the whole hot path in one C-ABI call ------------------------
-    def render_trajectory(self, traj, first_frame=0, total_frames=None, want_vis=False, max_batch=8, stretch=True):
+    def render_trajectory(self, traj, first_frame=0, total_frames=None, want_vis=False, max_batch=16, stretch=True, out_rgba=None):
         """traj: (F,N,3|6) array (numpy/CPU tensor -> pcr_render_frames_host with copies overlapped;
         CUDA tensor -> pcr_render_frames).  Frame f uses compute_camera_position(first_frame+f).
         stretch=True rescales the 220-frame camera schedule to total_frames."""
@@ -273,13 +277,20 @@ class TrajectoryBallRenderer(PointCloudRenderer):
         eng = _engine(self.DEVICE, n, self.width, self.height, batch=min(max_batch, max(F, 1)))
         if isinstance(traj, torch.Tensor) and traj.is_cuda:
             radius, rgb = self._per_point(n, traj.device)
-            return eng.render_frames(traj.contiguous(), cams, style, radius=radius, rgb=rgb, want_vis=want_vis)
+            return eng.render_frames(traj.contiguous(), cams, style, radius=radius, rgb=rgb, want_vis=want_vis, out_rgba=out_rgba)
         t = torch.as_tensor(traj)
         radius = None if self.radius is None or np.ndim(self.radius) == 0 else np.ascontiguousarray(self.radius, np.float32)
         rgb = None if self.user_rgb is None else np.ascontiguousarray(self.user_rgb, np.float32)
         out_vis = torch.empty((F, self.height, self.width), dtype=torch.int64).pin_memory() if want_vis else None
-        rgba = eng.render_frames_host(t.contiguous(), cams, style, radius_host=radius, rgb_host=rgb, out_vis=out_vis)
+        rgba = eng.render_frames_host(t.contiguous(), cams, style, radius_host=radius, rgb_host=rgb, out_vis=out_vis, out_rgba=out_rgba)
         return (rgba, out_vis) if want_vis else rgba
+
+
+    def render_trajectory_to_files(self, traj, output_folder=None, first_frame=0, total_frames=None, stem=None, chunk=16, writer=None):
+        """Render a trajectory and write one PNG per frame with the reference's naming rule; encoding
+        runs on a thread pool while the GPU renders the next chunk (output.render_to_files)."""
+        from .output import render_to_files
+        return render_to_files(self, traj, output_folder or self.output_folder or self.folder, first_frame, total_frames, stem, chunk, writer)
 
 
 class FixedFrame199Renderer(TrajectoryBallRenderer):

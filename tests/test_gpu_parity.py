@@ -7,6 +7,8 @@ f64, rounded once) and within ref_atol() of the reference; velocities / min / ma
 sRGB8 images within 1 code value and PSNR >= 50 dB of the oracle's f64 evaluation of the same
 shading model."""
 
+import os
+
 import numpy as np
 import pytest
 
@@ -425,3 +427,21 @@ def test_large_film_uses_global_atomic_binning(lib, orc):
             assert c.counters()["overflow_frames"] == 0
     finally:
         c.close()
+
+
+def test_trajectory_to_files_output_stage(tmp_path, orc):
+    """§8f-3: render_trajectory_to_files = host-buffer render + thread-pool PNG encode; the files
+    decode to exactly the frames the device path produces, with the reference's naming rule."""
+    from PIL import Image
+    from pointcloud_render_b200 import renderers
+    F, n = 7, 3000
+    traj = synthetic.trajectory(F, n, 6, seed=8)
+    r = renderers.TrajB1Renderer(None, output_folder=str(tmp_path / "render"), width=320, height=200)
+    paths = r.render_trajectory_to_files(traj, first_frame=196, total_frames=220, chunk=3)
+    want = r.render_trajectory(torch.from_numpy(traj).cuda(), first_frame=196, total_frames=220).cpu().numpy()
+    names = [os.path.basename(p) for p in paths]
+    assert names == ["frame_0196.png", "frame_0197.png", "frame_0198.png", "frame_0199.png",
+                     "frame_0200_b0.png", "frame_0201_b0.png", "frame_0202_b0.png"]
+    for k, p in enumerate(paths):
+        np.testing.assert_array_equal(np.asarray(Image.open(p)), want[k][..., :3])
+    renderers.release_engines()

@@ -134,3 +134,24 @@ def test_finalize_stats_follows_reference_roundings(orc, dtype):
     np.testing.assert_allclose(st[:3], np.mean(x, axis=0), rtol=1e-6 if dtype == np.float32 else 1e-14)
     out = ((x - st[:3].astype(dtype)) / dtype(st[9])).astype(np.float32)
     np.testing.assert_allclose(out, orc.standardize_point_cloud(x), atol=2e-7)
+
+
+def test_async_writer_and_naming(tmp_path):
+    """Output stage: frames > 199 are named frame_XXXX_b0 by every trajectory
+    class (traj_ball_renderer.py:376); the writer pool produces the same bytes as a direct save."""
+    from PIL import Image
+    from pointcloud_render_b200 import output
+    assert output.trajectory_frame_name("frame_0042_b1", 42) == "frame_0042_b1"
+    assert output.trajectory_frame_name("frame_0199_b1", 205) == "frame_0205_b0"
+    rng = np.random.default_rng(0)
+    frames = rng.integers(0, 255, (6, 40, 64, 4), dtype=np.uint8)
+    with output.AsyncImageWriter(workers=3) as w:
+        futs = [w.submit(str(tmp_path / "out" / f"f{k}"), frames[k]) for k in range(6)]
+        assert len(w.drain()) == 6 and all(f.done() for f in futs)
+    for k in range(6):
+        np.testing.assert_array_equal(np.asarray(Image.open(tmp_path / "out" / f"f{k}.png")), frames[k][..., :3])
+    with output.AsyncImageWriter(fmt="npy") as w:
+        w.submit(str(tmp_path / "raw"), frames[0])
+    np.testing.assert_array_equal(np.load(tmp_path / "raw.npy"), frames[0][..., :3])
+    with pytest.raises(ValueError):
+        output.AsyncImageWriter(fmt="bmp")
