@@ -5,6 +5,7 @@ Run here (the reference cannot travel to the GPU box):  python -m oracle.gen_gol
 What gets pinned:
   standardize.npz   standardize_point_cloud / transform_coordinates outputs of every flavour
   camera.npz        compute_camera_position of every script at characteristic frames
+  trails.npz        tail / head control points of the curve files _add_velocity_trail writes
   scene_*.npz       the scene generate_xml_content emits (centres, radius, reflectance, sensor,
                     floor, emitter), parsed back by oracle/scene_from_xml.py
   vis_example.npz   visibility ids of the C oracle for the example scene at 200x150 and the
@@ -96,6 +97,34 @@ def main():
         rr = cls("f.npy")
         q = rr.transform_coordinates(rr.standardize_point_cloud(x3.copy()))
         dump(name, rr.generate_xml_content(q, frame_index=frame, total_frames=220), x3, frame)
+
+    # ---- 8f-1: velocity trails = the control points the reference writes to temp_curves/*.txt ---
+    import tempfile
+    tg = {}
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            for name, cls, frame in (("traj_ball", ball.TrajectoryBallRenderer, 7), ("traj_vel", vel.TrajectoryVelRenderer, 211),
+                                     ("traj_b0", b0.FixedFrame199Renderer, 4), ("traj_ball", ball.TrajectoryBallRenderer, 150)):
+                rng = np.random.default_rng(frame)
+                x = (rng.standard_normal((200, 6)) * [1, 1, 1, 4, 4, 4]).astype(np.float32)
+                x[5, 3:] = 0
+                x[6, 3:] = [30, -40, 5]
+                rr = cls("f.npy")
+                pcl = rr.transform_coordinates(rr.standardize_point_cloud(x.copy()))
+                tails, heads, valid = np.zeros((200, 3), np.float32), np.zeros((200, 3), np.float32), np.zeros(200, bool)
+                for idx, pt in enumerate(pcl):
+                    segs = []
+                    rr._add_velocity_trail(segs, pt[:3], pt[3:6], point_index=idx, frame_index=frame)
+                    if segs:
+                        rows = np.loadtxt(rr.curve_files[-1])
+                        tails[idx], heads[idx], valid[idx] = rows[0, :3], rows[-1, :3], True
+                key = f"{name}_{frame}"
+                tg[f"raw_{key}"], tg[f"pcl_{key}"], tg[f"tail_{key}"], tg[f"head_{key}"], tg[f"valid_{key}"] = x, pcl, tails, heads, valid
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(OUT, "trails.npz"), **tg)
 
     # ---- oracle self-pin (unpinned by the reference) -----------------------------------------
     pos4 = np.concatenate([sc_ex["centers"], sc_ex["radius"][:, None]], axis=1).astype(np.float32)

@@ -144,6 +144,54 @@ def camera_position(preset, frame_index=0, total_frames=220, last_motion_frame=1
     return _lerp3(keys[1], keys[2], (frame_index - last_motion_frame) / max(fade_frames, 1))
 
 
+# --------------------------------------------------------------------------- 8f-1 trails
+TRAIL_RADIUS = 0.0007                      # traj_ball_renderer.py:160
+TRAIL_RGB = (0.2, 1.0, 0.4)                # traj_ball_renderer.py:179
+TRAIL_LEN = (0.07, 0.3)                    # base / max trail length, traj_ball_renderer.py:132-133
+
+
+def trail_length_scale(preset, frame_index):
+    """length_scale of _add_velocity_trail: traj_ball_renderer.py:119-124 (ramp-in over frames 0-19),
+    traj_vel_renderer.py:215-224 (ramp-in, then fade-out over 200-219), traj_original.py:78 /
+    traj_b0.py:127 / traj_b1.py:127 (always 1).  Python floats, f64."""
+    if preset in ("traj_original", "traj_b0", "traj_b1"):
+        return 1.0
+    if frame_index <= 19:
+        return frame_index / 19.0
+    if preset == "traj_vel" and frame_index > 199:
+        return 1.0 - (frame_index - 199) / 20
+    return 1.0
+
+
+def round6(x, exact=False):
+    """The `{:.6f}` text round trip of the reference's curve files (traj_ball_renderer.py:176).
+    exact=True formats every value like python does; the default is rint(x*1e6)/1e6 in f64, which is
+    what the CUDA path computes and agrees with the text round trip except on astronomically rare
+    near-ties (tests assert agreement on their data)."""
+    x = np.asarray(x, np.float64)
+    if exact:
+        return np.array([float(f"{v:.6f}") for v in x.ravel()], np.float64).reshape(x.shape)
+    return np.rint(x * 1e6) / 1e6
+
+
+def velocity_trails(pcl6, length_scale, exact_text=False):
+    """_add_velocity_trail (traj_ball_renderer.py:98-188) for a transformed (N,6) f32 array: the
+    straight trail from  position + (-v/|v|) * L  to  position,  L = (0.07 + 0.23*min(|v|/10,1)) *
+    length_scale, all in f64, both ends then pass through the 6-decimal text file and are read as
+    f32.  Returns tail (N,3) f32, head (N,3) f32, valid (N,) bool (|v| >= 1e-6 and length_scale > 0).
+    The 19 interior control points are collinear (to 5e-7) and are not modelled."""
+    pcl6 = np.asarray(pcl6, np.float32)
+    pos = pcl6[:, :3].astype(np.float64)
+    vel = pcl6[:, 3:6].astype(np.float64)
+    vn = np.sqrt((vel[:, 0] * vel[:, 0] + vel[:, 1] * vel[:, 1]) + vel[:, 2] * vel[:, 2])
+    valid = (vn >= 1e-6) & (length_scale > 0)
+    safe = np.where(valid, vn, 1.0)
+    length = (TRAIL_LEN[0] + (TRAIL_LEN[1] - TRAIL_LEN[0]) * np.minimum(vn / 10.0, 1.0)) * length_scale
+    direction = -vel / safe[:, None]
+    tail = pos + direction * length[:, None] * 1.0
+    return (round6(tail, exact_text).astype(np.float32), round6(pos, exact_text).astype(np.float32), valid)
+
+
 # scene constants per script: XMLTemplates HEAD/TAIL (SURVEY.md §7.3, all [R])
 PRESETS = {
     "example": dict(target=(0.0, 0.0, 0.0), fov=30.0, flip_x=True, floor_z=-0.2,
@@ -204,6 +252,12 @@ def lib():
         L.orc_shade.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32,
                                 ctypes.c_int, ctypes.POINTER(Frame), ctypes.POINTER(Scene), ctypes.c_void_p]
         L.orc_shade.restype = None
+        L.orc_visibility_caps.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32, ctypes.POINTER(Frame),
+                                          ctypes.c_void_p, ctypes.c_int]
+        L.orc_visibility_caps.restype = None
+        L.orc_shade_caps.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32,
+                                     ctypes.POINTER(ctypes.c_float), ctypes.POINTER(Frame), ctypes.POINTER(Scene), ctypes.c_void_p]
+        L.orc_shade_caps.restype = None
         L.orc_num_threads.restype = ctypes.c_int
         _lib = L
     return _lib
@@ -249,6 +303,34 @@ def shade(vis, pos4, attr4, frame, scene, id_base=0, owner_only=False):
     lib().orc_shade(vis.ctypes.data, pos4.ctypes.data, attr4.ctypes.data, pos4.shape[0], int(id_base),
                     int(owner_only), ctypes.byref(frame), ctypes.byref(scene), rgba.ctypes.data)
     return rgba
+
+
+def _caps(tail, head, valid, radius):
+    tail = np.asarray(tail, np.float32).reshape(-1, 3)
+    head = np.asarray(head, np.float32).reshape(-1, 3)
+    a4 = np.ascontiguousarray(np.concatenate([tail, np.full((len(tail), 1), radius, np.float32)], axis=1))
+    b4 = np.ascontiguousarray(np.concatenate([head, np.asarray(valid, np.float32).reshape(-1, 1)], axis=1))
+    return a4, b4
+
+
+def add_trails(vis, tail, head, valid, frame, cap_id_base, radius=TRAIL_RADIUS, brute_force=False):
+    """Merge the trails (capsules tail->head) into the (H,W) uint64 key buffer `vis`; trail j has
+    id cap_id_base + j.  Returns a new array."""
+    a4, b4 = _caps(tail, head, valid, radius)
+    out = np.ascontiguousarray(vis, np.uint64).copy()
+    lib().orc_visibility_caps(a4.ctypes.data, b4.ctypes.data, a4.shape[0], int(cap_id_base), ctypes.byref(frame),
+                              out.ctypes.data, 0 if brute_force else 1)
+    return out
+
+
+def shade_trails(rgba, vis, tail, head, valid, frame, scene, cap_id_base, radius=TRAIL_RADIUS, rgb=TRAIL_RGB):
+    a4, b4 = _caps(tail, head, valid, radius)
+    out = np.ascontiguousarray(rgba, np.uint8).copy()
+    vis = np.ascontiguousarray(vis, np.uint64)
+    c = (ctypes.c_float * 3)(*rgb)
+    lib().orc_shade_caps(vis.ctypes.data, a4.ctypes.data, b4.ctypes.data, a4.shape[0], int(cap_id_base), c,
+                         ctypes.byref(frame), ctypes.byref(scene), out.ctypes.data)
+    return out
 
 
 def num_threads():

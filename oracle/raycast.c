@@ -158,6 +158,87 @@ static int sphere_bbox(const orc_frame* f, const float* c, float r, int* i0, int
     return 1;
 }
 
+/* ---- velocity trails: a trail is the straight `linearcurve` the reference emits
+ * from  position - v_hat * L  to  position  with radius 0.0007 (traj_ball_renderer.py:98-188),
+ * modelled as a capsule = cylinder body + the two end spheres.  "VA-2": the body test below is a
+ * fixed binary32 operation sequence shared with the CUDA kernel (capsule_body_depth in
+ * pcr_kernels.cuh).  It is the cancellation-free form of the ray-cylinder quadratic: with
+ * P = v x d, T = d . (A x v) (a scalar triple product built from the small moment components),
+ * the discriminant is dd * (r^2 |P|^2 - T^2). -------------------------------------------------- */
+static inline int capsule_body_depth(const float* A, const float* B, float r2, float u, float w,
+                                     float near_clip, float far_clip, float* depth)
+{
+    float dx = B[0] - A[0], dy = B[1] - A[1], dz = B[2] - A[2];
+    float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    float ma = fmaf(-A[2], w, A[1]);
+    float mb = fmaf(A[2], u, -A[0]);
+    float me = fmaf(A[0], w, -(A[1] * u));
+    float T = fmaf(dz, me, fmaf(dy, mb, dx * ma));
+    float px = fmaf(w, dz, -dy);
+    float py = fmaf(-u, dz, dx);
+    float pz = fmaf(u, dy, -(w * dx));
+    float PP = fmaf(pz, pz, fmaf(py, py, px * px));
+    float disc = fmaf(r2, PP, -(T * T));
+    if (!(disc >= 0.0f)) return 0;
+    float va = fmaf(A[1], w, fmaf(A[0], u, A[2]));
+    float vd = fmaf(dy, w, fmaf(dx, u, dz));
+    float da = fmaf(dz, A[2], fmaf(dy, A[1], dx * A[0]));
+    float PQ = fmaf(va, dd, -(vd * da));
+    float s = (PQ - sqrtf(dd * disc)) / PP;
+    float y = fmaf(s, vd, -da);
+    if (!(y >= 0.0f && y <= dd)) return 0;
+    if (!(s >= near_clip && s <= far_clip)) return 0;
+    *depth = s;
+    return 1;
+}
+
+/* nearest of body / end sphere A / end sphere B */
+static inline int capsule_depth(const float* A, const float* B, float r2, float u, float w, float vv, float inv_vv,
+                                float near_clip, float far_clip, float* depth)
+{
+    float t, best = INFINITY;
+    int hit = 0;
+    if (capsule_body_depth(A, B, r2, u, w, near_clip, far_clip, &t)) { best = t; hit = 1; }
+    if (sphere_depth(A[0], A[1], A[2], r2, u, w, vv, inv_vv, near_clip, far_clip, &t) && t < best) { best = t; hit = 1; }
+    if (sphere_depth(B[0], B[1], B[2], r2, u, w, vv, inv_vv, near_clip, far_clip, &t) && t < best) { best = t; hit = 1; }
+    *depth = best;
+    return hit;
+}
+
+/* conservative pixel bbox of a capsule: hull of the two end spheres' (unclamped) boxes */
+static int capsule_bbox(const orc_frame* f, const float* ca, const float* cb, float r, int* i0, int* i1, int* j0, int* j1)
+{
+    const int W = f->W, H = f->H;
+    if (!(isfinite(ca[0]) && isfinite(ca[1]) && isfinite(ca[2]) && isfinite(cb[0]) && isfinite(cb[1]) && isfinite(cb[2]) && isfinite(r))) return 0;
+    r = fabsf(r);
+    if (ca[2] + r < f->near_clip && cb[2] + r < f->near_clip) return 0;
+    if (ca[2] - r <= 1e-3f || cb[2] - r <= 1e-3f) { *i0 = 0; *i1 = W - 1; *j0 = 0; *j1 = H - 1; return 1; }
+    double lo_i = 1e30, hi_i = -1e30, lo_j = 1e30, hi_j = -1e30;
+    for (int e = 0; e < 2; ++e) {
+        const float* c = e ? cb : ca;
+        double cz = c[2], rr = (double)r * 1.0001 + 1e-7;
+        double den = cz * cz - rr * rr;
+        double sx = rr * sqrt(c[0] * (double)c[0] + den), sy = rr * sqrt(c[1] * (double)c[1] + den);
+        double umin = (c[0] * cz - sx) / den, umax = (c[0] * cz + sx) / den;
+        double wmin = (c[1] * cz - sy) / den, wmax = (c[1] * cz + sy) / den;
+        double inv = 1.0 / (2.0 * (double)f->TW);
+        double fi0 = ((double)f->T - umax) * inv - 0.5, fi1 = ((double)f->T - umin) * inv - 0.5;
+        double fj0 = ((double)f->Th - wmax) * inv - 0.5, fj1 = ((double)f->Th - wmin) * inv - 0.5;
+        if (fi0 < lo_i) lo_i = fi0;
+        if (fi1 > hi_i) hi_i = fi1;
+        if (fj0 < lo_j) lo_j = fj0;
+        if (fj1 > hi_j) hi_j = fj1;
+    }
+    double a0 = ceil(lo_i - 0.01), a1 = floor(hi_i + 0.01), b0 = ceil(lo_j - 0.01), b1 = floor(hi_j + 0.01);
+    if (a0 < 0) a0 = 0;
+    if (b0 < 0) b0 = 0;
+    if (a1 > W - 1) a1 = W - 1;
+    if (b1 > H - 1) b1 = H - 1;
+    if (!(a0 <= a1 && b0 <= b1)) return 0;
+    *i0 = (int)a0; *i1 = (int)a1; *j0 = (int)b0; *j1 = (int)b1;
+    return 1;
+}
+
 /*
  * Visibility buffer.  pos4 = n x (x,y,z,r) world-space spheres (what BALL_SEGMENT emits);
  * vis = H*W keys, row 0 on top.  mode 0: brute force, every pixel against every sphere
@@ -243,6 +324,60 @@ void orc_visibility(const float* pos4, int64_t n, uint32_t id_base, const orc_fr
         }
         free(box);
     }
+    free(cam);
+}
+
+/*
+ * Merge m capsules (trails) into an existing visibility buffer: cap_a4 = m x (ax,ay,az,r),
+ * cap_b4 = m x (bx,by,bz,valid) in WORLD space; capsule j gets id cap_id_base + j.  mode 0: every
+ * pixel against every capsule; mode 1: bbox-accelerated, threads own row bands.
+ */
+void orc_visibility_caps(const float* cap_a4, const float* cap_b4, int64_t m, uint32_t cap_id_base, const orc_frame* f,
+                         uint64_t* vis, int mode)
+{
+    const int W = f->W, H = f->H;
+    float* cam = (float*)malloc((size_t)(m > 0 ? m : 1) * 8 * sizeof(float));
+    int* box = (int*)malloc((size_t)(m > 0 ? m : 1) * 4 * sizeof(int));
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < m; ++k) {
+        float* c = cam + 8 * k;
+        int* b = box + 4 * k;
+        to_camera(f, cap_a4 + 4 * k, c);
+        to_camera(f, cap_b4 + 4 * k, c + 4);
+        float r = cap_a4[4 * k + 3];
+        c[3] = r * r; c[7] = r;
+        int ok = cap_b4[4 * k + 3] != 0.0f;
+        if (ok && mode == 1) ok = capsule_bbox(f, c, c + 4, r, b, b + 1, b + 2, b + 3);
+        else if (ok) { b[0] = 0; b[1] = W - 1; b[2] = 0; b[3] = H - 1; }
+        if (!ok) { b[0] = 1; b[1] = 0; b[2] = 1; b[3] = 0; }
+    }
+    const int band = 8;
+    const int nb = (H + band - 1) / band;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int bi = 0; bi < nb; ++bi) {
+        int r0 = bi * band, r1 = r0 + band - 1;
+        if (r1 > H - 1) r1 = H - 1;
+        for (int64_t k = 0; k < m; ++k) {
+            const int* b = box + 4 * k;
+            int j0 = b[2] > r0 ? b[2] : r0, j1 = b[3] < r1 ? b[3] : r1;
+            if (j0 > j1 || b[0] > b[1]) continue;
+            const float* c = cam + 8 * k;
+            for (int j = j0; j <= j1; ++j) {
+                float w = pix_w(f, j);
+                for (int i = b[0]; i <= b[1]; ++i) {
+                    float u = pix_u(f, i);
+                    float vv = fmaf(u, u, fmaf(w, w, 1.0f));
+                    float inv_vv = 1.0f / vv;
+                    float t;
+                    if (!capsule_depth(c, c + 4, c[3], u, w, vv, inv_vv, f->near_clip, f->far_clip, &t)) continue;
+                    uint64_t key = ((uint64_t)f2u(t) << 32) | (uint64_t)(cap_id_base + (uint32_t)k);
+                    uint64_t* dst = vis + (size_t)j * W + i;
+                    if (key < *dst) *dst = key;
+                }
+            }
+        }
+    }
+    free(box);
     free(cam);
 }
 
@@ -355,6 +490,53 @@ void orc_shade(const uint64_t* vis, const float* pos4, const float* attr4, int64
             }
             if (write) { px[0] = srgb8(rgb[0]); px[1] = srgb8(rgb[1]); px[2] = srgb8(rgb[2]); px[3] = 255; }
             else { px[0] = px[1] = px[2] = px[3] = 0; }
+        }
+    }
+}
+
+/*
+ * Shade the pixels won by capsules (ids cap_id_base .. cap_id_base+m-1) on top of an image produced by
+ * orc_shade: diffuse trail colour, normal = from the nearest point of the capsule axis to the hit.
+ */
+void orc_shade_caps(const uint64_t* vis, const float* cap_a4, const float* cap_b4, int64_t m, uint32_t cap_id_base,
+                    const float trail_rgb[3], const orc_frame* f, const orc_scene* s, uint8_t* rgba)
+{
+    const int W = f->W, H = f->H;
+    const double up[3] = { 0.0, 0.0, 1.0 };
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int j = 0; j < H; ++j) {
+        float w = pix_w(f, j);
+        for (int i = 0; i < W; ++i) {
+            uint64_t key = vis[(size_t)j * W + i];
+            uint32_t id = (uint32_t)(key & 0xFFFFFFFFu);
+            if (id < cap_id_base || (int64_t)(id - cap_id_base) >= m || id >= ORC_ID_FLOOR) continue;
+            int64_t k = id - cap_id_base;
+            float t = u2f((uint32_t)(key >> 32));
+            float u = pix_u(f, i);
+            float dwx = fmaf(w, f->U[0], fmaf(u, f->L[0], f->D[0]));
+            float dwy = fmaf(w, f->U[1], fmaf(u, f->L[1], f->D[1]));
+            float dwz = fmaf(w, f->U[2], fmaf(u, f->L[2], f->D[2]));
+            double P[3] = { (double)fmaf(t, dwx, f->O[0]), (double)fmaf(t, dwy, f->O[1]), (double)fmaf(t, dwz, f->O[2]) };
+            const float* A = cap_a4 + 4 * k;
+            const float* B = cap_b4 + 4 * k;
+            double d[3] = { (double)B[0] - A[0], (double)B[1] - A[1], (double)B[2] - A[2] };
+            double dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+            double h = dd > 0.0 ? ((P[0] - A[0]) * d[0] + (P[1] - A[1]) * d[1] + (P[2] - A[2]) * d[2]) / dd : 0.0;
+            if (h < 0.0) h = 0.0;
+            if (h > 1.0) h = 1.0;
+            double nr[3] = { P[0] - (A[0] + h * d[0]), P[1] - (A[1] + h * d[1]), P[2] - (A[2] + h * d[2]) };
+            double l = sqrt(nr[0] * nr[0] + nr[1] * nr[1] + nr[2] * nr[2]);
+            if (l > 0.0) { nr[0] /= l; nr[1] /= l; nr[2] /= l; } else { nr[2] = 1.0; }
+            double Ld = (double)s->radiance * rect_form_factor(P, nr, s->light_half, s->light_z);
+            double Li = 0.0;
+            if (s->has_floor) {
+                double Pf[3] = { P[0], P[1], (double)s->floor_z };
+                double Bn = (double)s->floor_albedo * (double)s->radiance * rect_form_factor(Pf, up, s->light_half, s->light_z);
+                Li = (double)s->bounce * Bn * 0.5 * (1.0 - nr[2]);
+            }
+            uint8_t* px = rgba + ((size_t)j * W + i) * 4;
+            for (int ch = 0; ch < 3; ++ch) px[ch] = srgb8((double)trail_rgb[ch] * (Ld + Li));
+            px[3] = 255;
         }
     }
 }

@@ -150,3 +150,69 @@ def test_emitter_form_factor_known_value(orc):
         lin = expect
         srgb = 1.055 * lin ** (1 / 2.4) - 0.055
         assert abs(int(img[2, 2, 0]) - round(srgb * 255)) <= 1 and img[2, 2, 3] == 255
+
+
+@pytest.mark.parametrize("key,preset", [("traj_ball_7", "traj_ball"), ("traj_vel_211", "traj_vel"), ("traj_b0_4", "traj_b0"),
+                                        ("traj_ball_150", "traj_ball")])
+def test_velocity_trails_golden(golden, orc, key, preset):
+    """Trail end points against the reference's own curve files (tests/golden/trails.npz)."""
+    g = golden("trails.npz")
+    frame = int(key.rsplit("_", 1)[1])
+    pcl = orc.transform_coordinates(orc.standardize_point_cloud(g[f"raw_{key}"]), orc.PRESETS[preset]["flip_x"])
+    np.testing.assert_array_equal(pcl, g[f"pcl_{key}"])
+    for exact in (True, False):
+        tail, head, valid = orc.velocity_trails(pcl, orc.trail_length_scale(preset, frame), exact_text=exact)
+        v = g[f"valid_{key}"]
+        np.testing.assert_array_equal(valid, v)
+        np.testing.assert_array_equal(tail[v], g[f"tail_{key}"][v])
+        np.testing.assert_array_equal(head[v], g[f"head_{key}"][v])
+
+
+def test_trail_length_scale_schedules(orc):
+    assert [orc.trail_length_scale("traj_ball", f) for f in (0, 19, 20, 199, 219)] == [0.0, 1.0, 1.0, 1.0, 1.0]
+    assert orc.trail_length_scale("traj_vel", 209) == 0.5 and orc.trail_length_scale("traj_vel", 219) == 0.0
+    assert orc.trail_length_scale("traj_vel", 10) == 10 / 19.0
+    assert all(orc.trail_length_scale(p, f) == 1.0 for p in ("traj_original", "traj_b0", "traj_b1") for f in (0, 5, 205))
+
+
+def test_capsule_visibility_modes_agree_and_known_answers(orc):
+    """The capsule (trail) caster: bbox mode == brute force; a thick capsule across the view has the
+    silhouette of a stadium of the right width; thin reference-size trails hit pixels along the line."""
+    W, H = 160, 120
+    frame = orc.camera_frame((0, -4, 0), (0, 0, 0), (0, 0, 1), 40.0, 0.1, 100.0, W, H)
+    scene = orc.make_scene(has_floor=False)
+    base = orc.visibility(np.zeros((0, 4), np.float32), frame, scene)
+    rng = np.random.default_rng(0)
+    tail = rng.uniform(-1, 1, (40, 3)).astype(np.float32)
+    head = (tail + rng.uniform(-0.4, 0.4, (40, 3))).astype(np.float32)
+    valid = np.ones(40, bool)
+    valid[3] = False
+    a = orc.add_trails(base, tail, head, valid, frame, 100, radius=0.02, brute_force=True)
+    b = orc.add_trails(base, tail, head, valid, frame, 100, radius=0.02)
+    np.testing.assert_array_equal(a, b)
+    ids = (a & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    assert 103 not in ids and 100 in ids
+    # horizontal capsule of radius 0.25 and half-length 1 in the plane y = 0 (depth 4): height 2r, width 2(1+r)
+    one = orc.add_trails(base, np.float32([[-1, 0, 0]]), np.float32([[1, 0, 0]]), [True], frame, 7, radius=0.25, brute_force=True)
+    m = (one & np.uint64(0xFFFFFFFF)) == 7
+    px_per_unit = (W / 2) / np.tan(np.deg2rad(20.0)) / 4.0
+    rows, cols = np.nonzero(m.any(axis=1))[0], np.nonzero(m.any(axis=0))[0]
+    assert abs((rows.max() - rows.min() + 1) - 2 * 0.25 * px_per_unit) <= 2.5
+    assert abs((cols.max() - cols.min() + 1) - 2 * 1.25 * px_per_unit) <= 3.5
+    d = (one[H // 2, W // 2] >> np.uint64(32)).astype(np.uint32).view(np.float32)
+    assert abs(float(d) - 3.75) < 1e-3          # even W,H: the centre pixel ray is half a pixel off the axis
+    # an end-on capsule (ray parallel to the axis) is seen through its end sphere
+    end_on = orc.add_trails(base, np.float32([[0, 0, 0]]), np.float32([[0, 2, 0]]), [True], frame, 9, radius=0.3, brute_force=True)
+    assert (end_on[H // 2, W // 2] & np.uint64(0xFFFFFFFF)) == 9
+    # reference-size trails (r = 0.0007) are sub-pixel: at 1200 x 900 the 0.58-pixel-wide line is hit by
+    # roughly every second pixel-centre ray along it, and every hit lies on the projected segment
+    W2, H2 = 1200, 900
+    big = orc.camera_frame((0, -4, 0), (0, 0, 0), (0, 0, 1), 40.0, 0.1, 100.0, W2, H2)
+    base2 = orc.visibility(np.zeros((0, 4), np.float32), big, scene)
+    thin = orc.add_trails(base2, np.float32([[-1, 0, -0.5]]), np.float32([[1, 0, 0.5]]), [True], big, 11)
+    ys, xs = np.nonzero((thin & np.uint64(0xFFFFFFFF)) == 11)
+    ppu = (W2 / 2) / np.tan(np.deg2rad(20.0)) / 4.0
+    assert 0.3 * 2 * ppu < len(xs) <= 2 * ppu + 2
+    x_w = (xs + 0.5 - W2 / 2) / ppu
+    z_w = (H2 / 2 - 0.5 - ys) / ppu
+    assert np.abs(np.abs(z_w) - 0.5 * np.abs(x_w)).max() < 1.0 / ppu

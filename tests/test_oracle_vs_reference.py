@@ -97,3 +97,45 @@ def test_emitted_scene_round_trips(reference, orc):
         pr = orc.PRESETS[name]
         assert tuple(sc["target"]) == pr["target"] and sc["fov"] == pr["fov"]
         assert sc["floor_z"] == pr["floor_z"] and sc["floor_min"] == pr["floor_min"] and sc["floor_max"] == pr["floor_max"]
+
+
+def _reference_trails(cls, pcl6, frame_index, tmp_path, monkeypatch):
+    """Run the reference's own _add_velocity_trail for every point and read back the curve files
+    it writes (first and last control point = tail and head, as Mitsuba would load them)."""
+    monkeypatch.chdir(tmp_path)
+    r = cls("f.npy")
+    tails, heads, valid = [], [], []
+    for idx, pt in enumerate(pcl6):
+        segs = []
+        r._add_velocity_trail(segs, pt[:3], pt[3:6], point_index=idx, frame_index=frame_index)
+        if not segs:
+            valid.append(False); tails.append([0, 0, 0]); heads.append([0, 0, 0])
+            continue
+        rows = np.loadtxt(r.curve_files[-1])
+        assert rows.shape == (21, 4) and np.all(rows[:, 3] == 0.0007)
+        # interior control points are collinear with the ends to the file's 1e-6 resolution
+        tt = np.linspace(0, 1, 20)[:, None]
+        np.testing.assert_allclose(rows[:20, :3], rows[0, :3] + (rows[20, :3] - rows[0, :3]) * tt, atol=1.1e-6)
+        tails.append(rows[0, :3]); heads.append(rows[20, :3]); valid.append(True)
+    return np.float32(tails), np.float32(heads), np.array(valid)
+
+
+@pytest.mark.parametrize("name,frame_index", [("traj_ball", 0), ("traj_ball", 7), ("traj_ball", 150), ("traj_vel", 3),
+                                              ("traj_vel", 211), ("traj_vel", 219), ("traj_original", 199), ("traj_b0", 4), ("traj_b1", 205)])
+def test_velocity_trails_match_reference_curve_files(reference, orc, tmp_path, monkeypatch, name, frame_index):
+    """trail end points equal the control points the reference writes to its
+    temp_curves/*.txt files (what Mitsuba's linearcurve loader would read), bit for bit as f32."""
+    mod, cls = CLASSES[name]
+    rng = np.random.default_rng(frame_index)
+    x = (rng.standard_normal((300, 6)) * [1, 1, 1, 4, 4, 4]).astype(np.float32)
+    x[5, 3:] = 0                                   # no velocity -> no trail
+    x[6, 3:] = [30, -40, 5]                        # faster than the /10 normaliser -> clamped length
+    pcl = orc.transform_coordinates(orc.standardize_point_cloud(x), orc.PRESETS[name]["flip_x"])
+    t_ref, h_ref, v_ref = _reference_trails(getattr(reference[mod], cls), pcl, frame_index, tmp_path, monkeypatch)
+    scale = orc.trail_length_scale(name, frame_index)
+    for exact in (True, False):
+        tail, head, valid = orc.velocity_trails(pcl, scale, exact_text=exact)
+        np.testing.assert_array_equal(valid, v_ref)
+        np.testing.assert_array_equal(tail[valid], t_ref[valid])
+        np.testing.assert_array_equal(head[valid], h_ref[valid])
+    assert not v_ref[5] and (v_ref.sum() == (299 if scale > 0 else 0))
