@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PCR_ABI_VERSION 1
+#define PCR_ABI_VERSION 2
 
 /* Point ids stored in the low 32 bits of a visibility key. */
 #define PCR_ID_FLOOR 0xFFFFFFFEu
@@ -73,6 +73,9 @@ typedef struct pcr_camera {
     float far_clip;
     int32_t width;
     int32_t height;
+    double trail_scale; /* length_scale of _add_velocity_trail for THIS frame (traj_ball_renderer.py:119-124,
+                           traj_vel_renderer.py:215-224; 1.0 in traj_original/b0/b1); only read when
+                           pcr_style.trails is set; <= 0 draws no trails */
 } pcr_camera;
 
 /* Scene constants of XMLTemplates.BALL_SEGMENT / TAIL (example_renderer.py:41-72)
@@ -97,6 +100,15 @@ typedef struct pcr_style {
                             1: none (standardise only) — lets the facade expose
                             standardize_point_cloud / transform_coordinates separately */
     int32_t mean_mode;   /* how the centre of standardize_point_cloud is summed (PCR_MEAN_*)      */
+    /* velocity trails (_add_velocity_trail, traj_ball_renderer.py:98-188): pcr_render_frames[_host] with
+     * 6-column frames draws, per point, the straight trail  position - v_hat*L -> position,
+     * L = (trail_len_min + (trail_len_max - trail_len_min) * min(|v|/vel_norm, 1)) * camera.trail_scale,
+     * as a capsule of radius trail_radius; its id in the visibility buffer is n + point index.   */
+    int32_t trails;          /* 0: none (default), 1: draw them                                   */
+    float trail_radius;      /* 0.0007  (traj_ball_renderer.py:160)                               */
+    float trail_rgb[3];      /* 0.2, 1.0, 0.4  (:179)                                             */
+    double trail_len_min;    /* 0.07 (:132) — doubles: the reference computes the length in f64   */
+    double trail_len_max;    /* 0.3  (:133)                                                       */
 } pcr_style;
 
 /* The reference's np.mean(axis=0) is a SEQUENTIAL sum in the input dtype (example_renderer.py:96),
@@ -158,6 +170,14 @@ int pcr_standardize(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, in
  * pos' = (-+z, x, y + z_lift), vel' = (-+vz, vx, vy).  d_out must not alias d_in. */
 int pcr_transform_coordinates(pcr_ctx* ctx, const float* d_in, int64_t n, int cols, int flip_x,
                               float z_lift, float* d_out, void* stream);
+
+/* _add_velocity_trail's geometry alone (traj_ball_renderer.py:98-176): for an already transformed
+ * (n, 6) float32 array, the first and last control point of the curve file the reference writes
+ * for every point — tail = position - v_hat*L and head = position, both after the file's 6-decimal
+ * text round trip, as float32 — and whether the reference draws a trail at all (|v| >= 1e-6 and
+ * trail_scale > 0).  d_tail, d_head: [n][3] float32; d_valid: [n] uint8. */
+int pcr_velocity_trails(pcr_ctx* ctx, const float* d_pcl6, int64_t n, const pcr_style* style,
+                        double trail_scale, float* d_tail, float* d_head, uint8_t* d_valid, void* stream);
 
 /* K2+K3(+K4) — render already-transformed spheres (what generate_xml_content would emit).
  *   d_pos    [n] float4 (x,y,z,r) world space ; d_attr [n] float4 (r,g,b,_)

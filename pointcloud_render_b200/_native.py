@@ -24,7 +24,7 @@ SYMBOLS = (
     "pcr_abi_version", "pcr_create", "pcr_destroy", "pcr_last_error", "pcr_camera_frame",
     "pcr_standardize", "pcr_render", "pcr_shade", "pcr_render_frames", "pcr_render_frames_host",
     "pcr_zmin", "pcr_zmerge_nccl", "pcr_stats_partial", "pcr_standardize_with_stats", "pcr_counters",
-    "pcr_transform_coordinates", "pcr_profile", "pcr_profile_read", "pcr_kernel_name", "pcr_set_occlusion", "pcr_finalize_stats",
+    "pcr_transform_coordinates", "pcr_profile", "pcr_profile_read", "pcr_kernel_name", "pcr_set_occlusion", "pcr_finalize_stats", "pcr_velocity_trails",
 )
 
 
@@ -32,7 +32,7 @@ class Camera(ctypes.Structure):
     """pcr_camera — the <sensor> block of XMLTemplates.HEAD (example_renderer.py:16-31)."""
     _fields_ = [("origin", ctypes.c_float * 3), ("target", ctypes.c_float * 3), ("up", ctypes.c_float * 3),
                 ("fov_x_deg", ctypes.c_float), ("near_clip", ctypes.c_float), ("far_clip", ctypes.c_float),
-                ("width", ctypes.c_int32), ("height", ctypes.c_int32)]
+                ("width", ctypes.c_int32), ("height", ctypes.c_int32), ("trail_scale", ctypes.c_double)]
 
 
 class Style(ctypes.Structure):
@@ -42,7 +42,9 @@ class Style(ctypes.Structure):
                 ("has_floor", ctypes.c_int32), ("floor_z", ctypes.c_float), ("floor_min", ctypes.c_float * 2),
                 ("floor_max", ctypes.c_float * 2), ("floor_albedo", ctypes.c_float), ("light_z", ctypes.c_float),
                 ("light_half", ctypes.c_float), ("radiance", ctypes.c_float), ("bounce", ctypes.c_float),
-                ("xform", ctypes.c_int32), ("mean_mode", ctypes.c_int32)]
+                ("xform", ctypes.c_int32), ("mean_mode", ctypes.c_int32), ("trails", ctypes.c_int32),
+                ("trail_radius", ctypes.c_float), ("trail_rgb", ctypes.c_float * 3),
+                ("trail_len_min", ctypes.c_double), ("trail_len_max", ctypes.c_double)]
 
 
 class Frame(ctypes.Structure):
@@ -87,6 +89,7 @@ def load_library():
     L.pcr_transform_coordinates.argtypes = [vp, vp, i64, i32, i32, ctypes.c_float, vp, vp]
     L.pcr_set_occlusion.argtypes = [vp, i32, i32, i64]
     L.pcr_finalize_stats.argtypes = [vp, vp, i32, i64, i32, vp, vp]
+    L.pcr_velocity_trails.argtypes = [vp, vp, i64, styp, ctypes.c_double, vp, vp, vp, vp]
     L.pcr_profile.argtypes = [vp, i32]
     L.pcr_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), i32]
     L.pcr_kernel_name.argtypes = [i32]
@@ -100,19 +103,21 @@ def load_library():
 
 
 def make_camera(origin, target, up=(0.0, 0.0, 1.0), fov_x_deg=30.0, near_clip=0.1, far_clip=100.0,
-                width=1920, height=1080):
+                width=1920, height=1080, trail_scale=0.0):
     c = Camera()
     c.origin = (ctypes.c_float * 3)(*[float(x) for x in origin])
     c.target = (ctypes.c_float * 3)(*[float(x) for x in target])
     c.up = (ctypes.c_float * 3)(*[float(x) for x in up])
     c.fov_x_deg, c.near_clip, c.far_clip = float(fov_x_deg), float(near_clip), float(far_clip)
     c.width, c.height = int(width), int(height)
+    c.trail_scale = float(trail_scale)
     return c
 
 
 def make_style(color_mode=COLOR_CONST, const_rgb=(0.3, 0.3, 0.3), radius=0.01, flip_x=True, z_lift=0.0125,
                vel_norm=10.0, has_floor=True, floor_z=-0.2, floor_min=(-10.0, -10.0), floor_max=(10.0, 10.0),
-               floor_albedo=1.0, light_z=15.0, light_half=8.0, radiance=4.0, bounce=1.0, xform=0, mean_mode=MEAN_AUTO):
+               floor_albedo=1.0, light_z=15.0, light_half=8.0, radiance=4.0, bounce=1.0, xform=0, mean_mode=MEAN_AUTO,
+               trails=False, trail_radius=0.0007, trail_rgb=(0.2, 1.0, 0.4), trail_len_min=0.07, trail_len_max=0.3):
     s = Style()
     s.color_mode = int(color_mode)
     s.const_rgb = (ctypes.c_float * 3)(*const_rgb)
@@ -122,6 +127,9 @@ def make_style(color_mode=COLOR_CONST, const_rgb=(0.3, 0.3, 0.3), radius=0.01, f
     s.floor_max = (ctypes.c_float * 2)(*floor_max)
     s.floor_albedo, s.light_z, s.light_half = float(floor_albedo), float(light_z), float(light_half)
     s.radiance, s.bounce, s.xform, s.mean_mode = float(radiance), float(bounce), int(xform), int(mean_mode)
+    s.trails, s.trail_radius = int(bool(trails)), float(trail_radius)
+    s.trail_rgb = (ctypes.c_float * 3)(*trail_rgb)
+    s.trail_len_min, s.trail_len_max = float(trail_len_min), float(trail_len_max)
     return s
 
 
@@ -208,6 +216,18 @@ class Context:
         self._check(self.lib.pcr_transform_coordinates(self.handle, _ptr(pcl), n, cols, int(bool(flip_x)), float(z_lift),
                                                        _ptr(out), _stream_ptr(stream)))
         return out
+
+    def velocity_trails(self, pcl6, style, trail_scale, stream=None):
+        """(N,6) float32 CUDA tensor (transformed) -> tail (N,3), head (N,3) float32, valid (N,) uint8."""
+        import torch
+        assert pcl6.is_cuda and pcl6.is_contiguous() and pcl6.dtype == torch.float32 and pcl6.shape[1] == 6
+        n = pcl6.shape[0]
+        tail = torch.empty((n, 3), dtype=torch.float32, device=pcl6.device)
+        head = torch.empty((n, 3), dtype=torch.float32, device=pcl6.device)
+        valid = torch.empty(n, dtype=torch.uint8, device=pcl6.device)
+        self._check(self.lib.pcr_velocity_trails(self.handle, _ptr(pcl6), n, ctypes.byref(style), float(trail_scale), _ptr(tail),
+                                                 _ptr(head), _ptr(valid), _stream_ptr(stream)))
+        return tail, head, valid
 
     def stats_partial(self, pts, stream=None):
         import torch

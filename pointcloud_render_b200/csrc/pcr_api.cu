@@ -45,7 +45,8 @@ struct pcr_ctx {
     long long launches = 0;
 
     // scratch, all [max_batch][...]
-    float4* sph = nullptr;            // per survivor: camera-space sphere (cx, cy, cz, r)
+    float4* sph = nullptr;            // per survivor: camera-space sphere (cx, cy, cz, r) / capsule end A
+    float4* ext = nullptr;            // per survivor: capsule end B (trails)
     uint4* rect = nullptr;            // per survivor: pixel bbox + sphere index (K2a -> K2b, K3)
     unsigned int* surv_count = nullptr;
     int gx_cap = 0;
@@ -155,6 +156,9 @@ StyleDev to_style_dev(const pcr_style* s)
     for (int k = 0; k < 2; ++k) { d.floor_min[k] = s->floor_min[k]; d.floor_max[k] = s->floor_max[k]; }
     d.floor_albedo = s->floor_albedo; d.light_z = s->light_z; d.light_half = s->light_half;
     d.radiance = s->radiance; d.bounce = s->bounce; d.xform = s->xform;
+    d.trails = s->trails; d.trail_radius = s->trail_radius;
+    for (int k = 0; k < 3; ++k) d.trail_rgb[k] = s->trail_rgb[k];
+    d.trail_len_min = s->trail_len_min; d.trail_len_max = s->trail_len_max;
     return d;
 }
 
@@ -194,6 +198,7 @@ void to_frame_dev(const pcr_frame& f, FrameDev* d)
     d->near_clip = f.near_clip; d->far_clip = f.far_clip;
     d->W = f.W; d->H = f.H;
     d->tiles_x = (f.W + TILE - 1) / TILE; d->tiles_y = (f.H + TILE - 1) / TILE;
+    d->trail_scale = 0.0;
 }
 
 BinDev bin_of(pcr_ctx* c)
@@ -238,6 +243,7 @@ int upload_frames(pcr_ctx* ctx, const pcr_camera* cams, int nb, cudaStream_t str
         if (camera_frame_host(cams + b, &f) != PCR_OK) return fail(ctx, PCR_ERR_INVALID, "degenerate camera");
         if (f.W > ctx->max_w || f.H > ctx->max_h) return fail(ctx, PCR_ERR_CAPACITY, "frame larger than the context");
         to_frame_dev(f, h + b);
+        h[b].trail_scale = cams[b].trail_scale;
     }
     CK(cudaMemcpyAsync(ctx->d_frames, h, sizeof(FrameDev) * nb, cudaMemcpyHostToDevice, stream));
     CK(cudaEventRecord(ctx->ring_ev[slot], stream));
@@ -327,30 +333,35 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
     const int resident = ctx->num_sms * (2048 / BIN_THREADS);
     const int raster_ctas = ctx->num_sms * 4;          // k_raster_tiles: 4 CTAs of 256 threads resident per SM (register bound)
     unsigned long long* v = (unsigned long long*)vis;
+    // velocity trails (a second primitive per point) only exist in the fused whole-path entry
+    const int trails = raw && st.trails && raw->cols == 6 ? 1 : 0;
+    if (trails && 2 * (unsigned long long)n > 0xFFFFFFF0ull) return fail(ctx, PCR_ERR_INVALID, "too many points for trail ids (n + i)");
+    const uint32_t cap_id_base = trails ? (uint32_t)n : 0u;
+    const long long slots = 2 * ctx->max_points;       // survivor slots per frame: sphere + trail per point
 
     // one binning + raster pass over `np` spheres (sphere i = point i*step)
-    auto pass = [&](long long np, int step, const unsigned int* hz, int seeded) -> int {
+    auto pass = [&](long long np, int step, const unsigned int* hz, int seeded, int do_trails) -> int {
         unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((np + 2047) / 2048, std::max(1, 2 * resident / nb)));
         if (!use_smem) gx = (unsigned)std::max<long long>(1, (np + BIN_THREADS * 4 - 1) / (BIN_THREADS * 4));
         gx = std::min<unsigned>(gx, (unsigned)ctx->gx_cap);
         if (np > 0) {
             dim3 grid(gx, nb);
             const size_t sm = use_smem ? (size_t)tiles * 4 : 0;
-            if (!raw)
-                LAUNCH(KID_PROJECT, stream, (k_project_count<float, false><<<grid, BIN_THREADS, sm, stream>>>(
-                    pos, np, in_stride, raw_frames<float>(nullptr), st, step, ctx->d_frames, ctx->sph, ctx->rect, ctx->max_points, bin, use_smem, hz, ctx->hz_cap)));
-            else if (raw->is_f64)
-                LAUNCH(KID_PROJECT, stream, (k_project_count<double, true><<<grid, BIN_THREADS, sm, stream>>>(
-                    nullptr, np, 0, raw_frames<double>(raw), st, step, ctx->d_frames, ctx->sph, ctx->rect, ctx->max_points, bin, use_smem, hz, ctx->hz_cap)));
-            else
-                LAUNCH(KID_PROJECT, stream, (k_project_count<float, true><<<grid, BIN_THREADS, sm, stream>>>(
-                    nullptr, np, 0, raw_frames<float>(raw), st, step, ctx->d_frames, ctx->sph, ctx->rect, ctx->max_points, bin, use_smem, hz, ctx->hz_cap)));
+#define PCR_PROJECT(T, RAWB, TRB, posarg, strarg, rawarg)                                                                        \
+    LAUNCH(KID_PROJECT, stream, (k_project_count<T, RAWB, TRB><<<grid, BIN_THREADS, sm, stream>>>(                               \
+        posarg, np, strarg, rawarg, st, step, ctx->d_frames, ctx->sph, ctx->rect, ctx->ext, slots, bin, use_smem, hz, ctx->hz_cap)))
+            if (!raw) PCR_PROJECT(float, false, false, pos, in_stride, raw_frames<float>(nullptr));
+            else if (raw->is_f64 && do_trails) PCR_PROJECT(double, true, true, nullptr, 0, raw_frames<double>(raw));
+            else if (raw->is_f64) PCR_PROJECT(double, true, false, nullptr, 0, raw_frames<double>(raw));
+            else if (do_trails) PCR_PROJECT(float, true, true, nullptr, 0, raw_frames<float>(raw));
+            else PCR_PROJECT(float, true, false, nullptr, 0, raw_frames<float>(raw));
+#undef PCR_PROJECT
         }
         LAUNCH(KID_SCAN, stream, k_scan_tiles<<<nb, 1024, 0, stream>>>(ctx->d_frames, bin, np));
         if (np > 0) {
             dim3 grid(gx, nb);
             LAUNCH(KID_SCATTER, stream, k_scatter<<<grid, BIN_THREADS, use_smem ? tiles * 8 : 0, stream>>>(
-                np, ctx->d_frames, ctx->rect, ctx->max_points, bin, use_smem));
+                np, ctx->d_frames, ctx->sph, ctx->rect, ctx->ext, slots, bin, use_smem, st.trail_radius));
         }
         if (!seeded) {
             // floor keys of empty tiles, all-ones preset of split tiles
@@ -360,8 +371,12 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         if (np > 0) {
             // persistent raster: CTAs pull (tile, <= ITEM_SPHERES spheres) items from per-frame queues
             dim3 grid((unsigned)std::max(1, std::min(raster_ctas, tiles * nb)));
-            LAUNCH(KID_RASTER, stream, k_raster_tiles<<<grid, RASTER_THREADS, 0, stream>>>(
-                ctx->d_frames, st, ctx->sph, ctx->rect, ctx->max_points, bin, id_base, (uint32_t)step, v, vis_stride, nb, np, seeded, (int)gx));
+            if (do_trails)
+                LAUNCH(KID_RASTER, stream, k_raster_tiles<true><<<grid, RASTER_THREADS, 0, stream>>>(
+                    ctx->d_frames, st, ctx->sph, ctx->rect, ctx->ext, slots, bin, id_base, (uint32_t)step, cap_id_base, v, vis_stride, nb, np, seeded, (int)gx));
+            else
+                LAUNCH(KID_RASTER, stream, k_raster_tiles<false><<<grid, RASTER_THREADS, 0, stream>>>(
+                    ctx->d_frames, st, ctx->sph, ctx->rect, ctx->ext, slots, bin, id_base, (uint32_t)step, 0u, v, vis_stride, nb, np, seeded, (int)gx));
         }
         return PCR_OK;
     };
@@ -370,15 +385,15 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
     if (occl && n > ctx->occlusion_step) {
         // occluder pre-pass (every step-th point, true ids) -> Hi-Z -> main pass seeded with its keys
         const int step = ctx->occlusion_step;
-        int rc = pass((n + step - 1) / step, step, nullptr, 0);
+        int rc = pass((n + step - 1) / step, step, nullptr, 0, 0);       // trails are never occluders
         if (rc) return rc;
         const int hzn = ((W + HZ_W - 1) / HZ_W) * ((H + HZ_H - 1) / HZ_H);
         dim3 grid((unsigned)((hzn + 255) / 256), nb);
         LAUNCH(KID_HIZ, stream, k_hiz<<<grid, 256, 0, stream>>>(ctx->d_frames, v, vis_stride, ctx->hz, ctx->hz_cap));
-        rc = pass(n, 1, ctx->hz, 1);
+        rc = pass(n, 1, ctx->hz, 1, trails);
         if (rc) return rc;
     } else {
-        int rc = pass(n, 1, nullptr, 0);
+        int rc = pass(n, 1, nullptr, 0, trails);
         if (rc) return rc;
     }
     if (rgba) return launch_shade(ctx, st, vis, vis_stride, pos, attr, in_stride, raw, n, nb, id_base, owner_only, W, H, rgba, rgba_stride, stream);
@@ -421,7 +436,7 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     pcr_ctx* ctx = new (std::nothrow) pcr_ctx();
     if (!ctx) return PCR_ERR_NOMEM;
     ctx->device = device; ctx->max_points = max_points; ctx->max_w = max_w; ctx->max_h = max_h; ctx->max_batch = max_batch;
-    ctx->pair_cap = pair_capacity > 0 ? pair_capacity : 8 * max_points + 65536;
+    ctx->pair_cap = pair_capacity > 0 ? pair_capacity : 12 * max_points + 65536;
     if (ctx->pair_cap > 0xFFFFFFF0ll) ctx->pair_cap = 0xFFFFFFF0ll;
     ctx->tiles_cap = (((max_w + TILE - 1) / TILE) * ((max_h + TILE - 1) / TILE) + 3) & ~3;   // multiple of 4: k_scan_tiles uses uint4
     ctx->item_cap = ctx->tiles_cap + (int)(ctx->pair_cap / ITEM_SPHERES) + 1;
@@ -435,14 +450,17 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     if (e == cudaSuccess) {
         ctx->num_sms = prop.multiProcessorCount;
         ctx->smem_optin = (int)std::min<size_t>(prop.sharedMemPerBlockOptin, 200 * 1024);
-        e = cudaFuncSetAttribute(k_project_count<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+        e = cudaFuncSetAttribute(k_project_count<float, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<float, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<float, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<double, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<double, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
     }
 #define ALLOC(ptr, bytes) if (e == cudaSuccess) e = cudaMalloc((void**)&(ptr), (bytes))
-    ALLOC(ctx->sph, sizeof(float4) * B * N);
-    ALLOC(ctx->rect, sizeof(uint4) * B * N);
+    ALLOC(ctx->sph, sizeof(float4) * B * N * 2);       // 2 survivor slots per point: its sphere and its trail
+    ALLOC(ctx->ext, sizeof(float4) * B * N * 2);
+    ALLOC(ctx->rect, sizeof(uint4) * B * N * 2);
     ctx->gx_cap = (int)std::max<long long>(2 * ctx->num_sms * (2048 / BIN_THREADS), (max_points + BIN_THREADS * 4 - 1) / (BIN_THREADS * 4)) + 1;
     ALLOC(ctx->surv_count, sizeof(unsigned int) * B * (size_t)ctx->gx_cap);
     ALLOC(ctx->partials, sizeof(double) * B * MAX_STAT_BLOCKS * 9);
@@ -482,7 +500,7 @@ void pcr_destroy(pcr_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    void* frees[] = {ctx->surv_count, ctx->sph, ctx->rect, ctx->partials, ctx->stats, ctx->done, ctx->counts, ctx->offsets,
+    void* frees[] = {ctx->surv_count, ctx->ext, ctx->sph, ctx->rect, ctx->partials, ctx->stats, ctx->done, ctx->counts, ctx->offsets,
                      ctx->cursor, ctx->pairs, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
                      ctx->stage_rgba[0], ctx->stage_rgba[1], ctx->stage_vis[0], ctx->stage_vis[1], ctx->stage_radius, ctx->stage_rgb};
     for (void* p : frees) if (p) cudaFree(p);
@@ -571,6 +589,19 @@ int pcr_transform_coordinates(pcr_ctx* ctx, const float* d_in, int64_t n, int co
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
     LAUNCH(KID_AXIS, s, k_axis_transform<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_in, n, cols, flip_x, z_lift, d_out));
+    return PCR_OK;
+}
+
+int pcr_velocity_trails(pcr_ctx* ctx, const float* d_pcl6, int64_t n, const pcr_style* style, double trail_scale, float* d_tail,
+                        float* d_head, uint8_t* d_valid, void* stream)
+{
+    int rc = check_common(ctx, n, 6, style);
+    if (rc) return rc;
+    if (n == 0) return PCR_OK;
+    if (!d_pcl6 || !d_tail || !d_head || !d_valid) return fail(ctx, PCR_ERR_INVALID, "pcr_velocity_trails: NULL buffer");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    LAUNCH(KID_AXIS, s, k_trail_ends<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_pcl6, n, to_style_dev(style), trail_scale, d_tail, d_head, d_valid));
     return PCR_OK;
 }
 

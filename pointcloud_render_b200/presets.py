@@ -42,6 +42,13 @@ class RenderConfig:
     radiance: float = 4.0
     floor_albedo: float = 1.0         # diffuseReflectance of surfaceMaterial
     bounce: float = 1.0
+    # velocity trails (_add_velocity_trail): 'ramp' = traj_ball_renderer.py:119-124, 'ramp_fade' =
+    # traj_vel_renderer.py:215-224, 'const' = traj_original.py:78 / traj_b0.py:127, None = the script draws none
+    trail_schedule: Optional[str] = None
+    trail_radius: float = 0.0007
+    trail_rgb: Vec3 = (0.2, 1.0, 0.4)
+    trail_len_min: float = 0.07
+    trail_len_max: float = 0.3
 
     def camera_position(self, frame_index=0, total_frames=220):
         """compute_camera_position of the script this preset mirrors (python floats, f64):
@@ -61,16 +68,32 @@ class RenderConfig:
             a, b = mid, end
         return tuple(a[k] + (b[k] - a[k]) * p for k in range(3))
 
+    def trail_length_scale(self, frame_index):
+        """length_scale of the script's _add_velocity_trail (python floats, f64); 0 when it draws none.
+        The 0-19 ramp and the 199/20 fade are literals of the reference (not stretched)."""
+        if self.trail_schedule is None:
+            return 0.0
+        if self.trail_schedule == "const":
+            return 1.0
+        if frame_index <= 19:
+            return frame_index / 19.0
+        if self.trail_schedule == "ramp_fade" and frame_index > 199:
+            return 1.0 - (frame_index - 199) / 20
+        return 1.0
+
     def camera(self, frame_index=0, total_frames=220, width=None, height=None):
         return _native.make_camera(self.camera_position(frame_index, total_frames), self.target, self.up, self.fov,
-                                   self.near_clip, self.far_clip, width or self.width, height or self.height)
+                                   self.near_clip, self.far_clip, width or self.width, height or self.height,
+                                   trail_scale=self.trail_length_scale(frame_index))
 
-    def style(self, color_mode=_native.COLOR_CONST, xform=0, mean_mode=_native.MEAN_AUTO):
+    def style(self, color_mode=_native.COLOR_CONST, xform=0, mean_mode=_native.MEAN_AUTO, trails=False):
         return _native.make_style(color_mode=color_mode, const_rgb=self.const_rgb, radius=self.radius,
                                   flip_x=self.flip_x, z_lift=self.z_lift, vel_norm=self.vel_norm, has_floor=True,
                                   floor_z=self.floor_z, floor_min=self.floor_min, floor_max=self.floor_max,
                                   floor_albedo=self.floor_albedo, light_z=self.light_z, light_half=self.light_half,
-                                  radiance=self.radiance, bounce=self.bounce, xform=xform, mean_mode=mean_mode)
+                                  radiance=self.radiance, bounce=self.bounce, xform=xform, mean_mode=mean_mode,
+                                  trails=trails and self.trail_schedule is not None, trail_radius=self.trail_radius,
+                                  trail_rgb=self.trail_rgb, trail_len_min=self.trail_len_min, trail_len_max=self.trail_len_max)
 
     def for_trajectory(self, n_frames):
         """Stretch the 220-frame schedule (199 motion + 20 fade) over an n_frames trajectory
@@ -91,17 +114,17 @@ PRESETS = {
     "traj": RenderConfig("traj", (0.0, 0.0, -0.05), 36.0, True, -0.5, (-10.0, -10.0), (10.0, 10.0), 256, dolly=True),
     # traj_ball_renderer.py:13-28,59-65,281-307
     "traj_ball": RenderConfig("traj_ball", (0.0, 0.0, -0.05), 36.0, True, -0.5, (-10.0, -10.0), (10.0, 10.0), 128,
-                              keys=_BALL_KEYS),
+                              keys=_BALL_KEYS, trail_schedule="ramp"),
     # traj_vel_renderer.py:13-28,59-65,381-407
     "traj_vel": RenderConfig("traj_vel", (0.0, 0.0, -0.05), 36.0, True, -0.5, (-10.0, -10.0), (10.0, 10.0), 128,
-                             keys=_BALL_KEYS),
+                             keys=_BALL_KEYS, trail_schedule="ramp_fade"),
     # traj_original.py:10-38,40-66 (TAIL inherited from traj_ball_renderer.py:59-65)
     "traj_original": RenderConfig("traj_original", (0.0, 0.0, -0.05), 36.0, False, -0.5, (-10.0, -10.0), (10.0, 10.0),
-                                  128, eye=(-1.8, -1.8, 1.8)),
+                                  128, eye=(-1.8, -1.8, 1.8), trail_schedule="const"),
     # traj_b0.py:10-60,84-115 — floor = [-1,1]^2 scaled by 20 then translated by (10,10,-0.8)
     "traj_b0": RenderConfig("traj_b0", (-0.02, 0.15, -0.05), 36.0, False, -0.8, (-10.0, -10.0), (30.0, 30.0), 128,
-                            keys=((-2.2, -3.3, 2.0), (-1.3, -2.5, 0.8), (-1.0, -2.0, 0.7))),
+                            keys=((-2.2, -3.3, 2.0), (-1.3, -2.5, 0.8), (-1.0, -2.0, 0.7)), trail_schedule="const"),
     # traj_b1.py:10-60,84-115
     "traj_b1": RenderConfig("traj_b1", (0.0, -0.02, 0.0), 36.0, False, -0.8, (-10.0, -10.0), (30.0, 30.0), 128,
-                            keys=((-3.5, -2.5, 2.8), (-2.3, -1.5, 1.2), (-2.0, -1.2, 1.0))),
+                            keys=((-3.5, -2.5, 2.8), (-2.3, -1.5, 1.2), (-2.0, -1.2, 1.0)), trail_schedule="const"),
 }

@@ -86,7 +86,7 @@ class PointCloudRenderer:
     WITH_VELOCITY = False            # load_point_cloud reads x,y,z only (example_renderer.py:108-109)
 
     def __init__(self, file_path, output_folder=None, width=None, height=None, color_mode=_native.COLOR_CONST,
-                 radius=None, user_rgb=None):
+                 radius=None, user_rgb=None, trails=False):
         self.file_path = file_path
         self.folder, full_filename = os.path.split(file_path) if file_path else ("", "")
         self.folder = self.folder or '.'
@@ -98,6 +98,7 @@ class PointCloudRenderer:
         self.color_mode = int(color_mode)
         self.radius = radius          # None -> the BALL_SEGMENT literal; float; or per-point array (extension)
         self.user_rgb = user_rgb
+        self.trails = bool(trails)    # draw the script's velocity trails (render_trajectory, 6-column frames)
 
     # ---- hooks the reference exposes ----------------------------------------------------
     @staticmethod
@@ -158,7 +159,7 @@ class PointCloudRenderer:
 
     # ---- the seam: render_scene / save_scene ---------------------------------------------
     def _style(self):
-        return self.config.style(color_mode=self.color_mode)
+        return self.config.style(color_mode=self.color_mode, trails=self.trails)
 
     def _per_point(self, n, device):
         import torch

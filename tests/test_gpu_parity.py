@@ -445,3 +445,98 @@ def test_trajectory_to_files_output_stage(tmp_path, orc):
     for k, p in enumerate(paths):
         np.testing.assert_array_equal(np.asarray(Image.open(p)), want[k][..., :3])
     renderers.release_engines()
+
+
+# ------------------------------------------------------------------------------- 8f-1 velocity trails
+@pytest.mark.parametrize("key,preset", [("traj_ball_7", "traj_ball"), ("traj_vel_211", "traj_vel"), ("traj_b0_4", "traj_b0"),
+                                        ("traj_ball_150", "traj_ball")])
+def test_trail_geometry_matches_reference_curve_files(ctx, orc, golden, key, preset):
+    """pcr_velocity_trails against the control points the reference itself wrote to its curve files
+    (tests/golden/trails.npz): tail, head and 'draws a trail' bit for bit."""
+    g = golden("trails.npz")
+    frame = int(key.rsplit("_", 1)[1])
+    cfg = PRESETS[preset]
+    assert cfg.trail_length_scale(frame) == orc.trail_length_scale(preset, frame)
+    tail, head, valid = ctx.velocity_trails(dev(g[f"pcl_{key}"]), cfg.style(trails=True), cfg.trail_length_scale(frame))
+    v = g[f"valid_{key}"]
+    np.testing.assert_array_equal(valid.cpu().numpy().astype(bool), v)
+    np.testing.assert_array_equal(tail.cpu().numpy()[v], g[f"tail_{key}"][v])
+    np.testing.assert_array_equal(head.cpu().numpy()[v], g[f"head_{key}"][v])
+    # and a larger random set against the oracle (itself pinned to the reference)
+    rng = np.random.default_rng(5)
+    pcl = (rng.standard_normal((50_000, 6)) * [0.2, 0.2, 0.2, 5, 5, 5]).astype(np.float32)
+    for scale in (1.0, 7 / 19.0):
+        t2, h2, v2 = ctx.velocity_trails(dev(pcl), cfg.style(trails=True), scale)
+        wt, wh, wv = orc.velocity_trails(pcl, scale)
+        np.testing.assert_array_equal(v2.cpu().numpy().astype(bool), wv)
+        np.testing.assert_array_equal(t2.cpu().numpy()[wv], wt[wv])
+        np.testing.assert_array_equal(h2.cpu().numpy()[wv], wh[wv])
+
+
+@pytest.mark.parametrize("preset,frame_index,W,H,n,radius", [
+    ("traj_ball", 150, 1920, 1080, 4000, None),        # the reference's 0.0007 radius at its native film size
+    ("traj_ball", 7, 1024, 1024, 20_000, None),        # ramp-in (7/19 of the full length)
+    ("traj_vel", 211, 1024, 768, 3000, 0.004),         # fade-out; thicker trails cover many pixels
+    ("traj_b0", 60, 1024, 1024, 16384, 0.002),         # C3-like, per-point sphere radius
+    ("traj_original", 199, 333, 211, 2000, 0.01),      # ragged film, fat capsules
+])
+def test_trails_visibility_and_image_match_oracle(ctx, orc, preset, frame_index, W, H, n, radius):
+    """Whole path with velocity trails: keys (spheres, trails = ids n+i, floor) bit-exact against the
+    oracle's sphere + capsule caster, image within one code value."""
+    import dataclasses
+    cfg = PRESETS[preset]
+    if radius is not None:
+        cfg = dataclasses.replace(cfg, trail_radius=radius)
+    traj = synthetic.trajectory(2, n, 6, seed=frame_index)
+    rad = synthetic.radii(n) if preset == "traj_b0" else None
+    cams = [cfg.camera(frame_index + k, 220, W, H) for k in range(2)]
+    style = cfg.style(trails=True)
+    rgba, vis = ctx.render_frames(dev(traj), cams, style, radius=None if rad is None else dev(rad), want_vis=True)
+    sc = orc_scene(orc, cfg)
+    for k in range(2):
+        pcl = orc.transform_coordinates(orc.standardize_point_cloud(traj[k]), cfg.flip_x)
+        r = rad if rad is not None else np.full(n, cfg.radius, np.float32)
+        pos4 = np.concatenate([pcl[:, :3], r[:, None]], axis=1)
+        fr = orc_frame(orc, cfg, frame_index + k, 220, W, H)
+        tail, head, valid = orc.velocity_trails(pcl, cfg.trail_length_scale(frame_index + k))
+        want = orc.add_trails(orc.visibility(pos4, fr, sc), tail, head, valid, fr, n, radius=cfg.trail_radius)
+        got = keys(vis[k])
+        bad = np.argwhere(got != want)
+        assert len(bad) == 0, f"frame {k}: {len(bad)} pixels differ, first {bad[:3].tolist()}"
+        ids = (want & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        assert np.any((ids >= n) & (ids < 2 * n)), "the scene should show some trail pixels"
+        attr4 = orc.compute_color(pcl, mode=0)
+        img = orc.shade_trails(orc.shade(want, pos4, attr4, fr, sc), want, tail, head, valid, fr, sc, n, radius=cfg.trail_radius, rgb=cfg.trail_rgb)
+        check_image(rgba[k].cpu().numpy(), img)
+    # without the flag (or with 3-column frames) nothing changes: no id >= n appears
+    rgba0, vis0 = ctx.render_frames(dev(traj), cams, cfg.style(), radius=None if rad is None else dev(rad), want_vis=True)
+    ids0 = _native.keys_to_ids(vis0)
+    assert not np.any((ids0 >= n) & (ids0 < 0xFFFFFFFE))
+
+
+def test_trails_with_occlusion_prepass_and_overflow(lib, orc):
+    """Trails through the Hi-Z pre-pass (they are culled by it but are never occluders) and through
+    the pair_capacity overflow path."""
+    import dataclasses
+    n, W, H = 150_000, 1024, 768
+    cfg = dataclasses.replace(PRESETS["traj_ball"], trail_radius=0.002)
+    traj = synthetic.trajectory(1, n, 6, seed=3)
+    cams, style = [cfg.camera(120, 220, W, H)], cfg.style(trails=True, mean_mode=_native.MEAN_F64)
+    results = []
+    for mode, cap in ((0, 0), (1, 0), (1, 50_000)):
+        c = _native.Context(device=0, max_points=n, max_w=W, max_h=H, max_batch=1, pair_capacity=cap)
+        try:
+            c.set_occlusion(mode=mode)
+            rgba, vis = c.render_frames(dev(traj), cams, style, want_vis=True)
+            results.append((vis.clone(), rgba.clone(), c.counters()["overflow_frames"]))
+        finally:
+            c.close()
+    assert results[2][2] == 1 and results[0][2] == 0
+    for r in results[1:]:
+        assert torch.equal(results[0][0], r[0]) and torch.equal(results[0][1], r[1])
+    pcl = orc.transform_coordinates(orc.standardize_point_cloud(traj[0], exact_mean=True), True)
+    pos4 = np.concatenate([pcl[:, :3], np.full((n, 1), 0.01, np.float32)], axis=1)
+    fr = orc_frame(orc, cfg, 120, 220, W, H)
+    tail, head, valid = orc.velocity_trails(pcl, 1.0)
+    want = orc.add_trails(orc.visibility(pos4, fr, orc_scene(orc, cfg)), tail, head, valid, fr, n, radius=0.002)
+    np.testing.assert_array_equal(keys(results[0][0][0]), want)
