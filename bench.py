@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--points", type=int, default=0, help="override the workload's point count (C5 scaling studies)")
     ap.add_argument("--frames-per-step", type=int, default=0, help="frames per step per GPU (0 = workload default)")
     ap.add_argument("--ring", type=int, default=0, help="resident frames per GPU (0 = enough to exceed L2)")
+    ap.add_argument("--trails", action="store_true", help="also draw the reference's velocity trails (6-column workloads C3/C4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with events in the timed region")
@@ -364,7 +365,7 @@ def main():
     radius = torch.from_numpy(radius_np).cuda() if radius_np is not None else None
     ctx = _native.Context(device=local_rank, max_points=n, max_w=W, max_h=H, max_batch=min(B, 16))
     cams_all, cfg = cameras_for(spec, rank * 1000, ring)
-    style = cfg.style(color_mode=spec["color_mode"])
+    style = cfg.style(color_mode=spec["color_mode"], trails=args.trails and spec["cols"] == 6)
     rgba = torch.empty((B, H, W, 4), dtype=torch.uint8, device="cuda")
     host_rgba = torch.empty((B, H, W, 4), dtype=torch.uint8).pin_memory()
     slots = ring // B
@@ -476,7 +477,7 @@ def main():
     line = {"metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "mpoints_per_s": fps * n / 1e6,
-            "config": config_dict(args.workload, spec, ring, world),
+            "config": dict(config_dict(args.workload, spec, ring, world), trails=bool(args.trails and spec["cols"] == 6)),
             "e2e": e2e, "gpu_launches": int(launches), "kernels": kernels, "roofline": roofline,
             "clocks": sampler.summary() if sampler else None,
             "pairs_last_frame": counters["pairs_last_frame"], "overflow_frames": counters["overflow_frames"]}

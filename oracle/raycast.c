@@ -160,13 +160,13 @@ static int sphere_bbox(const orc_frame* f, const float* c, float r, int* i0, int
 
 /* ---- velocity trails: a trail is the straight `linearcurve` the reference emits
  * from  position - v_hat * L  to  position  with radius 0.0007 (traj_ball_renderer.py:98-188),
- * modelled as a capsule = cylinder body + the two end spheres.  "VA-2": the body test below is a
- * fixed binary32 operation sequence shared with the CUDA kernel (capsule_body_depth in
- * pcr_kernels.cuh).  It is the cancellation-free form of the ray-cylinder quadratic: with
+ * modelled as a capsule = cylinder body + the two end spheres.  "VA-2": the test below is a
+ * fixed binary32 operation sequence shared with the CUDA kernel (capsule_depth in pcr_kernels.cuh):
+ * body first; a ray that enters the infinite cylinder beyond an end can only hit that end's sphere.  It is the cancellation-free form of the ray-cylinder quadratic: with
  * P = v x d, T = d . (A x v) (a scalar triple product built from the small moment components),
  * the discriminant is dd * (r^2 |P|^2 - T^2). -------------------------------------------------- */
-static inline int capsule_body_depth(const float* A, const float* B, float r2, float u, float w,
-                                     float near_clip, float far_clip, float* depth)
+static inline int capsule_depth(const float* A, const float* B, float r2, float u, float w, float vv, float inv_vv,
+                                float near_clip, float far_clip, float* depth)
 {
     float dx = B[0] - A[0], dy = B[1] - A[1], dz = B[2] - A[2];
     float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
@@ -179,30 +179,30 @@ static inline int capsule_body_depth(const float* A, const float* B, float r2, f
     float pz = fmaf(u, dy, -(w * dx));
     float PP = fmaf(pz, pz, fmaf(py, py, px * px));
     float disc = fmaf(r2, PP, -(T * T));
-    if (!(disc >= 0.0f)) return 0;
-    float va = fmaf(A[1], w, fmaf(A[0], u, A[2]));
-    float vd = fmaf(dy, w, fmaf(dx, u, dz));
-    float da = fmaf(dz, A[2], fmaf(dy, A[1], dx * A[0]));
-    float PQ = fmaf(va, dd, -(vd * da));
-    float s = (PQ - sqrtf(dd * disc)) / PP;
-    float y = fmaf(s, vd, -da);
-    if (!(y >= 0.0f && y <= dd)) return 0;
-    if (!(s >= near_clip && s <= far_clip)) return 0;
-    *depth = s;
-    return 1;
-}
-
-/* nearest of body / end sphere A / end sphere B */
-static inline int capsule_depth(const float* A, const float* B, float r2, float u, float w, float vv, float inv_vv,
-                                float near_clip, float far_clip, float* depth)
-{
-    float t, best = INFINITY;
-    int hit = 0;
-    if (capsule_body_depth(A, B, r2, u, w, near_clip, far_clip, &t)) { best = t; hit = 1; }
-    if (sphere_depth(A[0], A[1], A[2], r2, u, w, vv, inv_vv, near_clip, far_clip, &t) && t < best) { best = t; hit = 1; }
-    if (sphere_depth(B[0], B[1], B[2], r2, u, w, vv, inv_vv, near_clip, far_clip, &t) && t < best) { best = t; hit = 1; }
-    *depth = best;
-    return hit;
+    if (!(disc >= 0.0f)) return 0;                  /* the ray misses the infinite cylinder, hence the capsule */
+    if (PP > 0.0f) {
+        float va = fmaf(A[1], w, fmaf(A[0], u, A[2]));
+        float vd = fmaf(dy, w, fmaf(dx, u, dz));
+        float da = fmaf(dz, A[2], fmaf(dy, A[1], dx * A[0]));
+        float PQ = fmaf(va, dd, -(vd * da));
+        float s = (PQ - sqrtf(dd * disc)) / PP;
+        float y = fmaf(s, vd, -da);
+        if (y >= 0.0f && y <= dd) {                 /* enters through the body: that is the nearest hit */
+            if (!(s >= near_clip && s <= far_clip)) return 0;
+            *depth = s;
+            return 1;
+        }
+        /* enters the cylinder beyond one end: only that end's sphere can be hit first */
+        const float* C = (y < 0.0f) ? A : B;
+        return sphere_depth(C[0], C[1], C[2], r2, u, w, vv, inv_vv, near_clip, far_clip, depth);
+    }
+    /* ray parallel to the axis: nearest of the two end spheres */
+    float ta, tb;
+    int ha = sphere_depth(A[0], A[1], A[2], r2, u, w, vv, inv_vv, near_clip, far_clip, &ta);
+    int hb = sphere_depth(B[0], B[1], B[2], r2, u, w, vv, inv_vv, near_clip, far_clip, &tb);
+    if (ha && (!hb || ta <= tb)) { *depth = ta; return 1; }
+    if (hb) { *depth = tb; return 1; }
+    return 0;
 }
 
 /* conservative pixel bbox of a capsule: hull of the two end spheres' (unclamped) boxes */

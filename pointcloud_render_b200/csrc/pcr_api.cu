@@ -436,7 +436,7 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     pcr_ctx* ctx = new (std::nothrow) pcr_ctx();
     if (!ctx) return PCR_ERR_NOMEM;
     ctx->device = device; ctx->max_points = max_points; ctx->max_w = max_w; ctx->max_h = max_h; ctx->max_batch = max_batch;
-    ctx->pair_cap = pair_capacity > 0 ? pair_capacity : 12 * max_points + 65536;
+    ctx->pair_cap = pair_capacity > 0 ? pair_capacity : 24 * max_points + 65536;
     if (ctx->pair_cap > 0xFFFFFFF0ll) ctx->pair_cap = 0xFFFFFFF0ll;
     ctx->tiles_cap = (((max_w + TILE - 1) / TILE) * ((max_h + TILE - 1) / TILE) + 3) & ~3;   // multiple of 4: k_scan_tiles uses uint4
     ctx->item_cap = ctx->tiles_cap + (int)(ctx->pair_cap / ITEM_SPHERES) + 1;
