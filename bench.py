@@ -189,6 +189,7 @@ def cpu_baseline(spec, ring_host, radius, budget_s=12.0, max_frames=40):
     from oracle import pcr_oracle as orc
     from pointcloud_render_b200.presets import PRESETS
     cfg = PRESETS[spec["preset"]].for_trajectory(spec["frames"])
+    orc.set_num_threads()                                       # all host cores, whatever OMP_NUM_THREADS says
     cpu_frame(orc, ring_host[0], cfg, 0, spec, radius)          # warm-up (page in, OpenMP pool)
     total, frames = 0.0, 0
     while frames < max_frames and total < budget_s:
@@ -210,6 +211,7 @@ def run_reference(args, spec, rank, world):
     from oracle import pcr_oracle as orc
     from pointcloud_render_b200.presets import PRESETS
     orc.build()
+    orc.set_num_threads()                                       # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
     cfg = PRESETS[spec["preset"]].for_trajectory(spec["frames"])
     frames_per_step = 2 if spec["points"] >= 500_000 else 4
     ring = max(4, frames_per_step * 2)

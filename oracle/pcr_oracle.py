@@ -259,6 +259,8 @@ def lib():
                                      ctypes.POINTER(ctypes.c_float), ctypes.POINTER(Frame), ctypes.POINTER(Scene), ctypes.c_void_p]
         L.orc_shade_caps.restype = None
         L.orc_num_threads.restype = ctypes.c_int
+        L.orc_set_num_threads.argtypes = [ctypes.c_int]
+        L.orc_set_num_threads.restype = None
         _lib = L
     return _lib
 
@@ -331,6 +333,12 @@ def shade_trails(rgba, vis, tail, head, valid, frame, scene, cap_id_base, radius
     lib().orc_shade_caps(vis.ctypes.data, a4.ctypes.data, b4.ctypes.data, a4.shape[0], int(cap_id_base), c,
                          ctypes.byref(frame), ctypes.byref(scene), out.ctypes.data)
     return out
+
+
+def set_num_threads(n=None):
+    """Use n OpenMP threads (default: every host CPU) regardless of OMP_NUM_THREADS."""
+    lib().orc_set_num_threads(int(n or os.cpu_count() or 1))
+    return num_threads()
 
 
 def num_threads():

@@ -541,6 +541,17 @@ void orc_shade_caps(const uint64_t* vis, const float* cap_a4, const float* cap_b
     }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm of bench.py asks for all cores */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    extern void omp_set_num_threads(int);
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void)
 {
     int n = 1;
