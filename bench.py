@@ -431,7 +431,20 @@ def main():
             step_host(args.warmup + s)
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": frames_total / e2e_s, "unit": "frames/s",
+        # context for the end-to-end number: what a bare pinned H2D copy of one step's input achieves on this box
+        cp0, cp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dst = torch.empty_like(resident[:B])
+        dst.copy_(host[:B], non_blocking=True)
+        torch.cuda.synchronize()
+        cp0.record()
+        for _ in range(3):
+            dst.copy_(host[:B], non_blocking=True)
+        cp1.record()
+        torch.cuda.synchronize()
+        h2d_gbs = 3 * B * spec["input_bytes_per_frame"] / (cp0.elapsed_time(cp1) * 1e-3) / 1e9
+        del dst
+        e2e = {"value": frames_total / e2e_s, "unit": "frames/s", "pcie_h2d_gbs_measured": h2d_gbs,
+               "h2d_copy_bound_frames_per_s": world * h2d_gbs * 1e9 / spec["input_bytes_per_frame"],
                "h2d_bytes_per_step": int(B * spec["input_bytes_per_frame"] + (n * 4 if spec["radii"] else 0)),
                "d2h_bytes_per_step": int(B * W * H * 4), "ms_per_step": e2e_s / args.steps * 1e3,
                "api": "pcr_render_frames_host (pinned host trajectory in, pinned host RGBA8 out; copies overlap kernels)"}
