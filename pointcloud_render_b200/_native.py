@@ -284,6 +284,9 @@ class Context:
         assert traj.is_cuda and traj.is_contiguous() and traj.dim() == 3
         F, n, cols = traj.shape
         assert len(cams) == F
+        if F == 0:
+            return (torch.empty((0, 0, 0, 4), dtype=torch.uint8, device=traj.device), None) if want_vis else \
+                torch.empty((0, 0, 0, 4), dtype=torch.uint8, device=traj.device)
         W, H = cams[0].width, cams[0].height
         cam_arr = (Camera * F)(*cams)
         rgba = out_rgba if out_rgba is not None else torch.empty((F, H, W, 4), dtype=torch.uint8, device=traj.device)

@@ -84,6 +84,12 @@ struct pcr_ctx {
 
     long long last_overflow_frames = 0;
 
+    // The scratch is shared by every entry point, so work issued on DIFFERENT streams must not
+    // overlap: each entry waits for the previous entry's last event when the stream changed.
+    cudaEvent_t ev_last = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool has_last = false;
+
     // stats-ahead pipeline of pcr_render_frames: K0 of batch k+1 runs on s_aux while batch k renders
     cudaStream_t s_aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_stats[2] = {}, ev_free[2] = {};
@@ -400,6 +406,22 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
     return PCR_OK;
 }
 
+// Serialise entries that use the context's scratch across streams (see pcr_ctx::ev_last).
+int enter(pcr_ctx* ctx, cudaStream_t s)
+{
+    if (ctx->has_last && ctx->last_stream != s) CK(cudaStreamWaitEvent(s, ctx->ev_last, 0));
+    return PCR_OK;
+}
+
+int leave(pcr_ctx* ctx, cudaStream_t s)
+{
+    if (!ctx->ev_last) CK(cudaEventCreateWithFlags(&ctx->ev_last, cudaEventDisableTiming));
+    CK(cudaEventRecord(ctx->ev_last, s));
+    ctx->last_stream = s;
+    ctx->has_last = true;
+    return PCR_OK;
+}
+
 int check_common(pcr_ctx* ctx, long long n, int cols, const pcr_style* style)
 {
     if (!ctx) return PCR_ERR_INVALID;
@@ -515,6 +537,7 @@ void pcr_destroy(pcr_ctx* ctx)
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_last) cudaEventDestroy(ctx->ev_last);
     for (int k = 0; k < 2; ++k) { if (ctx->ev_stats[k]) cudaEventDestroy(ctx->ev_stats[k]); if (ctx->ev_free[k]) cudaEventDestroy(ctx->ev_free[k]); }
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
@@ -529,9 +552,10 @@ int pcr_stats_partial(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, 
     if (rc) return rc;
     if (!d_in || !d_partial9 || n < 1) return fail(ctx, PCR_ERR_INVALID, "pcr_stats_partial: NULL buffer or n < 1");
     CK(cudaSetDevice(ctx->device));
+    if ((rc = enter(ctx, (cudaStream_t)stream))) return rc;
     int rc2 = launch_stats(ctx, d_in, in_is_f64, n, cols, 0, 1, ctx->partials, d_partial9, 2, (cudaStream_t)stream);
     if (rc2) return rc2;
-    return PCR_OK;
+    return leave(ctx, (cudaStream_t)stream);
 }
 
 int pcr_finalize_stats(pcr_ctx* ctx, const double* d_partials, int n_shards, int64_t n_total, int in_is_f64, double* d_stats10,
@@ -570,13 +594,14 @@ int pcr_standardize(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, in
     if (!d_in || !d_pos_out || !d_attr_out) return fail(ctx, PCR_ERR_INVALID, "pcr_standardize: NULL buffer");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = enter(ctx, s))) return rc;
     rc = launch_stats(ctx, d_in, in_is_f64, n, cols, 0, 1, ctx->partials, ctx->stats, 1, s, style->mean_mode);
     if (rc) return rc;
     rc = launch_transform(ctx, d_in, in_is_f64, n, cols, 0, 1, d_radius, d_rgb, ctx->stats, to_style_dev(style),
                           (float4*)d_pos_out, (float4*)d_attr_out, (float4*)d_vel_out, 0, s);
     if (rc) return rc;
     if (d_stats) CK(cudaMemcpyAsync(d_stats, ctx->stats, sizeof(double) * 10, cudaMemcpyDeviceToDevice, s));
-    return PCR_OK;
+    return leave(ctx, s);
 }
 
 int pcr_transform_coordinates(pcr_ctx* ctx, const float* d_in, int64_t n, int cols, int flip_x, float z_lift, float* d_out,
@@ -614,11 +639,14 @@ int pcr_render(pcr_ctx* ctx, const float* d_pos, const float* d_attr, int64_t n,
     if ((unsigned long long)id_base + (unsigned long long)n > 0xFFFFFFFEull) return fail(ctx, PCR_ERR_INVALID, "point id overflow");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = enter(ctx, s))) return rc;
     rc = upload_frames(ctx, cam, 1, s);
     if (rc) return rc;
     const long long px = (long long)cam->width * cam->height;
-    return launch_render(ctx, (const float4*)d_pos, (const float4*)d_attr, 0, nullptr, n, 1, id_base, to_style_dev(style), cam->width,
-                         cam->height, d_vis, px, d_rgba, px, 0, s);
+    rc = launch_render(ctx, (const float4*)d_pos, (const float4*)d_attr, 0, nullptr, n, 1, id_base, to_style_dev(style), cam->width,
+                       cam->height, d_vis, px, d_rgba, px, 0, s);
+    if (rc) return rc;
+    return leave(ctx, s);
 }
 
 int pcr_shade(pcr_ctx* ctx, const uint64_t* d_vis, const float* d_pos, const float* d_attr, int64_t n, uint32_t id_base,
@@ -629,13 +657,14 @@ int pcr_shade(pcr_ctx* ctx, const uint64_t* d_vis, const float* d_pos, const flo
     if (!cam || !d_vis || !d_rgba || (n > 0 && (!d_pos || !d_attr))) return fail(ctx, PCR_ERR_INVALID, "pcr_shade: NULL buffer");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = enter(ctx, s))) return rc;
     rc = upload_frames(ctx, cam, 1, s);
     if (rc) return rc;
     const long long px = (long long)cam->width * cam->height;
     rc = launch_shade(ctx, to_style_dev(style), d_vis, px, (const float4*)d_pos, (const float4*)d_attr, 0, nullptr, n, 1, id_base, owner_only,
                       cam->width, cam->height, d_rgba, px, s);
     if (rc) return rc;
-    return PCR_OK;
+    return leave(ctx, s);
 }
 
 int pcr_render_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols, int n_frames, const float* d_radius,
@@ -656,6 +685,7 @@ int pcr_render_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, 
     const size_t elem = in_is_f64 ? 8 : 4;
     const long long frame_stride = n * cols;
     if (!d_vis) { rc = ensure_vis(ctx); if (rc) return rc; }
+    if ((rc = enter(ctx, s))) return rc;
     const int B = ctx->max_batch;
     const int nbatches = (n_frames + B - 1) / B;
     // K0 (and the serial reference-exact mean, when selected) of batch k+1 runs on a second stream
@@ -713,7 +743,7 @@ int pcr_render_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, 
         if (rc) return rc;
         if (ahead) CK(cudaEventRecord(ctx->ev_free[k & 1], s));
     }
-    return PCR_OK;
+    return leave(ctx, s);
 }
 
 int pcr_render_frames_host(pcr_ctx* ctx, const void* h_in, int in_is_f64, int64_t n, int cols, int n_frames, const float* h_radius,
@@ -752,6 +782,9 @@ int pcr_render_frames_host(pcr_ctx* ctx, const void* h_in, int in_is_f64, int64_
         }
         ctx->stage_in_bytes = (size_t)B * frame_bytes;
     }
+    // earlier stream-ordered calls may still be using the scratch and the staging buffers
+    if ((rc = enter(ctx, ctx->s_h2d))) return rc;
+    if ((rc = enter(ctx, ctx->s_comp))) return rc;
     const float *d_radius = nullptr, *d_rgb = nullptr;
     if (h_radius) { CK(cudaMemcpyAsync(ctx->stage_radius, h_radius, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->s_comp)); d_radius = ctx->stage_radius; }
     if (h_rgb) { CK(cudaMemcpyAsync(ctx->stage_rgb, h_rgb, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->s_comp)); d_rgb = ctx->stage_rgb; }

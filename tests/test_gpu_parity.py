@@ -540,3 +540,41 @@ def test_trails_with_occlusion_prepass_and_overflow(lib, orc):
     tail, head, valid = orc.velocity_trails(pcl, 1.0)
     want = orc.add_trails(orc.visibility(pos4, fr, orc_scene(orc, cfg)), tail, head, valid, fr, n, radius=0.002)
     np.testing.assert_array_equal(keys(results[0][0][0]), want)
+
+
+def test_float64_frames_with_trails_device_and_host_entries(ctx, orc):
+    """float64 input through the fused path (K1 in f64, the reference's f64 sequential mean), with
+    trails, through both the device-buffer and the host-buffer entry; 9 frames over batches of 4
+    exercise the stats-ahead stream."""
+    import dataclasses
+    F, n, W, H = 9, 5000, 640, 480
+    cfg = dataclasses.replace(PRESETS["traj_vel"], trail_radius=0.003)
+    traj = synthetic.trajectory(F, n, 6, seed=12, dtype=np.float64) * 3.0 + 1.5
+    cams = [cfg.camera(195 + k, 220, W, H) for k in range(F)]           # crosses the fade-out of the trail length
+    style = cfg.style(trails=True, color_mode=2)
+    rgba, vis = ctx.render_frames(dev(traj), cams, style, want_vis=True)
+    host_vis = torch.empty((F, H, W), dtype=torch.int64).pin_memory()
+    host_rgba = ctx.render_frames_host(torch.from_numpy(traj).pin_memory(), cams, style, out_vis=host_vis)
+    assert torch.equal(host_vis, vis.cpu()) and torch.equal(host_rgba, rgba.cpu())
+    sc = orc_scene(orc, cfg)
+    for k in (0, 4, 8):
+        pcl = orc.transform_coordinates(orc.standardize_point_cloud(traj[k]), cfg.flip_x)
+        pos4 = np.concatenate([pcl[:, :3], np.full((n, 1), cfg.radius, np.float32)], axis=1)
+        fr = orc_frame(orc, cfg, 195 + k, 220, W, H)
+        tail, head, valid = orc.velocity_trails(pcl, cfg.trail_length_scale(195 + k))
+        want = orc.add_trails(orc.visibility(pos4, fr, sc), tail, head, valid, fr, n, radius=cfg.trail_radius)
+        np.testing.assert_array_equal(keys(vis[k]), want)
+        attr4 = orc.compute_color(pcl, mode=2)
+        img = orc.shade_trails(orc.shade(want, pos4, attr4, fr, sc), want, tail, head, valid, fr, sc, n, radius=cfg.trail_radius, rgb=cfg.trail_rgb)
+        check_image(rgba[k].cpu().numpy(), img)
+
+
+def test_zero_frames_and_tiny_inputs(ctx):
+    cfg = PRESETS["traj_ball"]
+    empty = torch.empty((0, 100, 3), dtype=torch.float32, device="cuda")
+    out = ctx.render_frames(empty, [], cfg.style())
+    assert tuple(out.shape) == (0, 1080, 1920, 4) or out.numel() == 0
+    one = torch.zeros((1, 1, 3), dtype=torch.float32, device="cuda")      # a single point: extent 0 -> NaN positions, like numpy
+    rgba, vis = ctx.render_frames(one, [cfg.camera(0, 220, 64, 48)], cfg.style(), want_vis=True)
+    ids = _native.keys_to_ids(vis)
+    assert np.all(ids >= 0xFFFFFFFE)                                      # nothing but floor / miss
