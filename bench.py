@@ -261,11 +261,15 @@ def run_point_sharded(args, spec, rank, world, local_rank):
     style, cam = cfg.style(color_mode=spec["color_mode"]), cfg.camera(0, 1, W, H)
     ctx = _native.Context(device=local_rank, max_points=b - a, max_w=W, max_h=H, max_batch=1)
 
+    bufs = sharding.point_sharded_buffers(b - a, cam, local.device)          # allocated once, reused every frame
+    frames1 = local.unsqueeze(0)
+
     def step():
         if world > 1:
-            return sharding.render_point_sharded(ctx, local, a, n, cam, style)
-        pos4, attr4 = ctx.standardize(local, style)
-        return ctx.render(pos4, attr4, cam, style)
+            return sharding.render_point_sharded(ctx, local, a, n, cam, style, buffers=bufs)
+        # one GPU: the whole-path entry (K1 fused into K2a / K4, nothing materialised)
+        rgba1, vis1 = ctx.render_frames(frames1, [cam], style, out_rgba=bufs["rgba"].unsqueeze(0), out_vis=bufs["vis"].unsqueeze(0))
+        return vis1[0], rgba1[0]
 
     def barrier():
         torch.cuda.synchronize()

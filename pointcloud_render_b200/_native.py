@@ -246,31 +246,32 @@ class Context:
                                                 _ptr(out), _stream_ptr(stream)))
         return out
 
-    def standardize_with_stats(self, pts, style, stats10, radius=None, rgb=None, stream=None):
+    def standardize_with_stats(self, pts, style, stats10, radius=None, rgb=None, stream=None, out=None):
+        """out = (pos4, attr4) reuses caller buffers (no allocation per call)."""
         import torch
         n, cols = pts.shape
-        pos = torch.empty((n, 4), dtype=torch.float32, device=pts.device)
-        attr = torch.empty((n, 4), dtype=torch.float32, device=pts.device)
+        pos = out[0] if out is not None else torch.empty((n, 4), dtype=torch.float32, device=pts.device)
+        attr = out[1] if out is not None else torch.empty((n, 4), dtype=torch.float32, device=pts.device)
         self._check(self.lib.pcr_standardize_with_stats(self.handle, _ptr(pts), int(pts.dtype == torch.float64), n, cols,
                                                         _ptr(radius), _ptr(rgb), ctypes.byref(style), _ptr(stats10),
                                                         _ptr(pos), _ptr(attr), None, _stream_ptr(stream)))
         return pos, attr
 
     # ---- K2..K4 ----------------------------------------------------------------------------
-    def render(self, pos4, attr4, cam, style, id_base=0, shade=True, stream=None):
+    def render(self, pos4, attr4, cam, style, id_base=0, shade=True, stream=None, out_vis=None, out_rgba=None):
         """pos4/attr4: (N,4) float32 CUDA -> vis (H,W) int64 view of the uint64 keys, rgba (H,W,4) uint8."""
         import torch
         n = pos4.shape[0]
         dev = pos4.device
-        vis = torch.empty((cam.height, cam.width), dtype=torch.int64, device=dev)
-        rgba = torch.empty((cam.height, cam.width, 4), dtype=torch.uint8, device=dev) if shade else None
+        vis = out_vis if out_vis is not None else torch.empty((cam.height, cam.width), dtype=torch.int64, device=dev)
+        rgba = (out_rgba if out_rgba is not None else torch.empty((cam.height, cam.width, 4), dtype=torch.uint8, device=dev)) if shade else None
         self._check(self.lib.pcr_render(self.handle, _ptr(pos4) if n else None, _ptr(attr4) if n else None, n, int(id_base),
                                         ctypes.byref(cam), ctypes.byref(style), _ptr(vis), _ptr(rgba), _stream_ptr(stream)))
         return vis, rgba
 
-    def shade(self, vis, pos4, attr4, cam, style, id_base=0, owner_only=False, stream=None):
+    def shade(self, vis, pos4, attr4, cam, style, id_base=0, owner_only=False, stream=None, out_rgba=None):
         import torch
-        rgba = torch.empty((cam.height, cam.width, 4), dtype=torch.uint8, device=vis.device)
+        rgba = out_rgba if out_rgba is not None else torch.empty((cam.height, cam.width, 4), dtype=torch.uint8, device=vis.device)
         n = pos4.shape[0]
         self._check(self.lib.pcr_shade(self.handle, _ptr(vis), _ptr(pos4) if n else None, _ptr(attr4) if n else None, n,
                                        int(id_base), int(owner_only), ctypes.byref(cam), ctypes.byref(style), _ptr(rgba),

@@ -396,6 +396,9 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         const int hzn = ((W + HZ_W - 1) / HZ_W) * ((H + HZ_H - 1) / HZ_H);
         dim3 grid((unsigned)((hzn + 255) / 256), nb);
         LAUNCH(KID_HIZ, stream, k_hiz<<<grid, 256, 0, stream>>>(ctx->d_frames, v, vis_stride, ctx->hz, ctx->hz_cap));
+        const int hzn2 = (((W + HZ_W - 1) / HZ_W + 3) / 4) * (((H + HZ_H - 1) / HZ_H + 3) / 4);
+        dim3 grid2((unsigned)((hzn2 + 255) / 256), nb);
+        LAUNCH(KID_HIZ, stream, k_hiz2<<<grid2, 256, 0, stream>>>(ctx->d_frames, ctx->hz, ctx->hz_cap));
         rc = pass(n, 1, ctx->hz, 1, trails);
         if (rc) return rc;
     } else {
@@ -462,7 +465,10 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     if (ctx->pair_cap > 0xFFFFFFF0ll) ctx->pair_cap = 0xFFFFFFF0ll;
     ctx->tiles_cap = (((max_w + TILE - 1) / TILE) * ((max_h + TILE - 1) / TILE) + 3) & ~3;   // multiple of 4: k_scan_tiles uses uint4
     ctx->item_cap = ctx->tiles_cap + (int)(ctx->pair_cap / ITEM_SPHERES) + 1;
-    ctx->hz_cap = ((max_w + HZ_W - 1) / HZ_W) * ((max_h + HZ_H - 1) / HZ_H);
+    {   // level 1 (8x4 pixel blocks) + level 2 (4x4 groups of them), see hiz_far_bits
+        const int w1 = (max_w + HZ_W - 1) / HZ_W, h1 = (max_h + HZ_H - 1) / HZ_H;
+        ctx->hz_cap = w1 * h1 + ((w1 + 3) / 4) * ((h1 + 3) / 4);
+    }
     if (const char* e = getenv("PCR_OCCLUSION")) ctx->occlusion = atoi(e);
     if (const char* e = getenv("PCR_OCCLUSION_STEP")) ctx->occlusion_step = std::max(2, atoi(e));
     const size_t B = (size_t)max_batch, N = (size_t)max_points, Tn = (size_t)ctx->tiles_cap;
