@@ -242,6 +242,18 @@ int pcr_standardize_with_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, in
                                const double* d_stats10, float* d_pos_out, float* d_attr_out,
                                float* d_vel_out, void* stream);
 
+/* Point-sharded whole path without materialising the transformed arrays (K1 fused into K2a / K4,
+ * like pcr_render_frames) for ONE shard of a cloud whose global stats are already known:
+ *   pcr_stats_partial -> all-gather -> pcr_finalize_stats -> pcr_render_shard -> z-merge ->
+ *   pcr_shade_shard(owner_only = 1) -> byte-MAX assembly.
+ * d_in: this shard's raw (n, cols) points; ids stored = id_base + local index.  No trails. */
+int pcr_render_shard(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols,
+                     const float* d_radius, const float* d_rgb, const double* d_stats10, uint32_t id_base,
+                     const pcr_camera* cam, const pcr_style* style, uint64_t* d_vis, void* stream);
+int pcr_shade_shard(pcr_ctx* ctx, const uint64_t* d_vis, const void* d_in, int in_is_f64, int64_t n, int cols,
+                    const float* d_radius, const float* d_rgb, const double* d_stats10, uint32_t id_base,
+                    int owner_only, const pcr_camera* cam, const pcr_style* style, uint8_t* d_rgba, void* stream);
+
 /* Counters of the last pcr_render / pcr_render_frames call (synchronises `stream`):
  * out[0] = kernels launched, out[1] = (tile,sphere) pairs of the last frame,
  * out[2] = frames that overflowed pair_capacity, out[3] = spheres culled (last frame). */

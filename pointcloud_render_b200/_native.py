@@ -24,7 +24,7 @@ SYMBOLS = (
     "pcr_abi_version", "pcr_create", "pcr_destroy", "pcr_last_error", "pcr_camera_frame",
     "pcr_standardize", "pcr_render", "pcr_shade", "pcr_render_frames", "pcr_render_frames_host",
     "pcr_zmin", "pcr_zmerge_nccl", "pcr_stats_partial", "pcr_standardize_with_stats", "pcr_counters",
-    "pcr_transform_coordinates", "pcr_profile", "pcr_profile_read", "pcr_kernel_name", "pcr_set_occlusion", "pcr_finalize_stats", "pcr_velocity_trails",
+    "pcr_transform_coordinates", "pcr_profile", "pcr_profile_read", "pcr_kernel_name", "pcr_set_occlusion", "pcr_finalize_stats", "pcr_velocity_trails", "pcr_render_shard", "pcr_shade_shard",
 )
 
 
@@ -89,6 +89,8 @@ def load_library():
     L.pcr_transform_coordinates.argtypes = [vp, vp, i64, i32, i32, ctypes.c_float, vp, vp]
     L.pcr_set_occlusion.argtypes = [vp, i32, i32, i64]
     L.pcr_finalize_stats.argtypes = [vp, vp, i32, i64, i32, vp, vp]
+    L.pcr_render_shard.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp, u32, camp, styp, vp, vp]
+    L.pcr_shade_shard.argtypes = [vp, vp, vp, i32, i64, i32, vp, vp, vp, u32, i32, camp, styp, vp, vp]
     L.pcr_velocity_trails.argtypes = [vp, vp, i64, styp, ctypes.c_double, vp, vp, vp, vp]
     L.pcr_profile.argtypes = [vp, i32]
     L.pcr_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), i32]
@@ -276,6 +278,25 @@ class Context:
         self._check(self.lib.pcr_shade(self.handle, _ptr(vis), _ptr(pos4) if n else None, _ptr(attr4) if n else None, n,
                                        int(id_base), int(owner_only), ctypes.byref(cam), ctypes.byref(style), _ptr(rgba),
                                        _stream_ptr(stream)))
+        return rgba
+
+    def render_shard(self, pts, stats10, cam, style, id_base=0, radius=None, rgb=None, out_vis=None, stream=None):
+        """One shard of a point-sharded cloud, fused path: raw (n, 3|6) points + global stats -> vis keys."""
+        import torch
+        n, cols = pts.shape
+        vis = out_vis if out_vis is not None else torch.empty((cam.height, cam.width), dtype=torch.int64, device=pts.device)
+        self._check(self.lib.pcr_render_shard(self.handle, _ptr(pts) if n else None, int(pts.dtype == torch.float64), n, cols, _ptr(radius),
+                                              _ptr(rgb), _ptr(stats10), int(id_base), ctypes.byref(cam), ctypes.byref(style), _ptr(vis),
+                                              _stream_ptr(stream)))
+        return vis
+
+    def shade_shard(self, vis, pts, stats10, cam, style, id_base=0, owner_only=True, radius=None, rgb=None, out_rgba=None, stream=None):
+        import torch
+        n, cols = pts.shape
+        rgba = out_rgba if out_rgba is not None else torch.empty((cam.height, cam.width, 4), dtype=torch.uint8, device=vis.device)
+        self._check(self.lib.pcr_shade_shard(self.handle, _ptr(vis), _ptr(pts) if n else None, int(pts.dtype == torch.float64), n, cols,
+                                             _ptr(radius), _ptr(rgb), _ptr(stats10), int(id_base), int(owner_only), ctypes.byref(cam),
+                                             ctypes.byref(style), _ptr(rgba), _stream_ptr(stream)))
         return rgba
 
     def render_frames(self, traj, cams, style, radius=None, rgb=None, want_vis=False, out_rgba=None, out_vis=None,

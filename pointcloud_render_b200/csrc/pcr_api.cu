@@ -673,6 +673,49 @@ int pcr_shade(pcr_ctx* ctx, const uint64_t* d_vis, const float* d_pos, const flo
     return leave(ctx, s);
 }
 
+int pcr_render_shard(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols, const float* d_radius, const float* d_rgb,
+                     const double* d_stats10, uint32_t id_base, const pcr_camera* cam, const pcr_style* style, uint64_t* d_vis,
+                     void* stream)
+{
+    int rc = check_common(ctx, n, cols, style);
+    if (rc) return rc;
+    if (!cam || !d_vis || !d_stats10 || (n > 0 && !d_in)) return fail(ctx, PCR_ERR_INVALID, "pcr_render_shard: NULL buffer");
+    if ((unsigned long long)id_base + (unsigned long long)n > 0xFFFFFFFEull) return fail(ctx, PCR_ERR_INVALID, "point id overflow");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = enter(ctx, s))) return rc;
+    rc = upload_frames(ctx, cam, 1, s);
+    if (rc) return rc;
+    StyleDev st = to_style_dev(style);
+    st.trails = 0;                                       // trail ids (n + i) are not defined across shards
+    const RawSrc raw = {d_in, in_is_f64, n * cols, cols, d_stats10, d_radius, d_rgb};
+    const long long px = (long long)cam->width * cam->height;
+    rc = launch_render(ctx, nullptr, nullptr, 0, &raw, n, 1, id_base, st, cam->width, cam->height, d_vis, px, nullptr, px, 0, s);
+    if (rc) return rc;
+    return leave(ctx, s);
+}
+
+int pcr_shade_shard(pcr_ctx* ctx, const uint64_t* d_vis, const void* d_in, int in_is_f64, int64_t n, int cols, const float* d_radius,
+                    const float* d_rgb, const double* d_stats10, uint32_t id_base, int owner_only, const pcr_camera* cam,
+                    const pcr_style* style, uint8_t* d_rgba, void* stream)
+{
+    int rc = check_common(ctx, n, cols, style);
+    if (rc) return rc;
+    if (!cam || !d_vis || !d_rgba || !d_stats10 || (n > 0 && !d_in)) return fail(ctx, PCR_ERR_INVALID, "pcr_shade_shard: NULL buffer");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = enter(ctx, s))) return rc;
+    rc = upload_frames(ctx, cam, 1, s);
+    if (rc) return rc;
+    StyleDev st = to_style_dev(style);
+    st.trails = 0;
+    const RawSrc raw = {d_in, in_is_f64, n * cols, cols, d_stats10, d_radius, d_rgb};
+    const long long px = (long long)cam->width * cam->height;
+    rc = launch_shade(ctx, st, d_vis, px, nullptr, nullptr, 0, &raw, n, 1, id_base, owner_only, cam->width, cam->height, d_rgba, px, s);
+    if (rc) return rc;
+    return leave(ctx, s);
+}
+
 int pcr_render_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols, int n_frames, const float* d_radius,
                       const float* d_rgb, const pcr_camera* cams, const pcr_style* style, uint64_t* d_vis, uint8_t* d_rgba,
                       void* stream)

@@ -94,26 +94,24 @@ def assemble_image_(rgba, group=None):
 def point_sharded_buffers(n_local, cam, device):
     """Reusable work buffers for render_point_sharded (avoids per-frame allocations)."""
     import torch
-    return {"pos4": torch.empty((n_local, 4), dtype=torch.float32, device=device),
-            "attr4": torch.empty((n_local, 4), dtype=torch.float32, device=device),
-            "vis": torch.empty((cam.height, cam.width), dtype=torch.int64, device=device),
+    return {"vis": torch.empty((cam.height, cam.width), dtype=torch.int64, device=device),
             "rgba": torch.empty((cam.height, cam.width, 4), dtype=torch.uint8, device=device)}
 
 
 def render_point_sharded(ctx, pts_local, id_base, n_total, cam, style, radius=None, rgb=None, group=None, shade=True, buffers=None):
-    """The whole point-sharded path on one rank: K0 partials -> C0 -> K1 -> K2/K3 -> C1 -> K4(owner)
+    """The whole point-sharded path on one rank: K0 partials -> C0 -> K2/K3 (K1 inlined) -> C1 -> K4(owner)
     -> byte MAX.  pts_local: (n_local, 3|6) CUDA tensor, this rank's slice of the n_total-point cloud.
     Stream-ordered, no host synchronisation."""
     import torch
     b = buffers or {}
     part = ctx.stats_partial(pts_local)
     stats = allgather_stats_device(ctx, part, n_total, pts_local.dtype == torch.float64, group)
-    pos4, attr4 = ctx.standardize_with_stats(pts_local, style, stats, radius=radius, rgb=rgb,
-                                             out=(b["pos4"], b["attr4"]) if b else None)
-    vis, _ = ctx.render(pos4, attr4, cam, style, id_base=id_base, shade=False, out_vis=b.get("vis"))
+    # fused: K1 is evaluated inside K2a (binning) and K4 (winners only); nothing is materialised
+    vis = ctx.render_shard(pts_local, stats, cam, style, id_base=id_base, radius=radius, rgb=rgb, out_vis=b.get("vis"))
     zmerge_(vis, group)
     if not shade:
         return vis, None
-    rgba = ctx.shade(vis, pos4, attr4, cam, style, id_base=id_base, owner_only=True, out_rgba=b.get("rgba"))
+    rgba = ctx.shade_shard(vis, pts_local, stats, cam, style, id_base=id_base, owner_only=True, radius=radius, rgb=rgb,
+                           out_rgba=b.get("rgba"))
     assemble_image_(rgba, group)
     return vis, rgba

@@ -314,6 +314,8 @@ def test_point_sharded_merge_equals_unsharded(ctx, orc):
         p4, a4 = ctx.standardize_with_stats(dev(x[a:b]), style, gstats_d)
         np.testing.assert_array_equal(p4.cpu().numpy(), pos4[a:b].cpu().numpy())
         v, _ = ctx.render(p4, a4, cam, style, id_base=a, shade=False)
+        # the fused shard entry (K1 inlined in K2a, nothing materialised) gives the same keys
+        assert torch.equal(ctx.render_shard(dev(x[a:b]), gstats_d, cam, style, id_base=a), v)
         parts.append((a, p4, a4))
         merged = v if merged is None else ctx.zmin_(merged, v)
     torch.cuda.synchronize()
@@ -321,6 +323,7 @@ def test_point_sharded_merge_equals_unsharded(ctx, orc):
     img = None
     for (a, p4, a4) in parts:
         part = ctx.shade(merged, p4, a4, cam, style, id_base=a, owner_only=True)
+        assert torch.equal(ctx.shade_shard(merged, dev(x[a:a + p4.shape[0]]), gstats_d, cam, style, id_base=a, owner_only=True), part)
         img = part if img is None else torch.maximum(img, part)
     np.testing.assert_array_equal(img.cpu().numpy(), rgba_full.cpu().numpy())
 
