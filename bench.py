@@ -95,6 +95,33 @@ def cameras_for(spec, first, count):
 
 
 # --------------------------------------------------------------------------------------------------
+# host placement
+def bind_to_gpu_numa(local_rank):
+    """Run this rank (and first-touch its pinned staging memory) on the NUMA node its GPU hangs off, when
+    the container lets us see that.  Pure placement: returns a small dict for the JSON line."""
+    info = {"bound": False}
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        info.update(pci=bdf, numa_node=node)
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(bound=True, cpus=len(allowed))
+    except Exception as e:          # placement is best effort
+        info["note"] = f"{type(e).__name__}: {e}"[:120]
+    return info
+
+
+# --------------------------------------------------------------------------------------------------
 # clocks
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -358,6 +385,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa(local_rank)                  # before the pinned trajectory is allocated
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B = spec["frames_per_step"]
@@ -498,7 +526,7 @@ def main():
             "dtype": "f32", "data": "synthetic", "mpoints_per_s": fps * n / 1e6,
             "config": dict(config_dict(args.workload, spec, ring, world), trails=bool(args.trails and spec["cols"] == 6)),
             "e2e": e2e, "gpu_launches": int(launches), "kernels": kernels, "roofline": roofline,
-            "clocks": sampler.summary() if sampler else None,
+            "clocks": sampler.summary() if sampler else None, "host_placement": numa,
             "pairs_last_frame": counters["pairs_last_frame"], "overflow_frames": counters["overflow_frames"]}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(spec, host_np, radius_np)
