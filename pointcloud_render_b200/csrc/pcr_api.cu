@@ -837,9 +837,9 @@ int pcr_render_frames_host(pcr_ctx* ctx, const void* h_in, int in_is_f64, int64_
     const float *d_radius = nullptr, *d_rgb = nullptr;
     if (h_radius) { CK(cudaMemcpyAsync(ctx->stage_radius, h_radius, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->s_comp)); d_radius = ctx->stage_radius; }
     if (h_rgb) { CK(cudaMemcpyAsync(ctx->stage_rgb, h_rgb, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->s_comp)); d_rgb = ctx->stage_rgb; }
-    // chunks of at most B frames, but at least ~4 chunks per call so that the H2D copy of chunk
+    // chunks of at most B frames, but at least ~8 chunks per call so that the H2D copy of chunk
     // k+1, the kernels of chunk k and the D2H copy of chunk k-1 overlap even for short calls
-    const int C = std::max(1, std::min(B, (n_frames + 3) / 4));
+    const int C = std::max(1, std::min(B, (n_frames + 7) / 8));
     int chunk = 0;
     for (int f0 = 0; f0 < n_frames; f0 += C, ++chunk) {
         const int nb = std::min(C, n_frames - f0);
