@@ -20,6 +20,15 @@ METRICS = [
     "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
     "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct",
     "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
+    # atomics: shared-memory (tile histograms / ranks), global ATOM (returning) and RED (non-returning), L2 side
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_atom.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_atom.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_atom.sum", "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_red.sum",
+    "l1tex__m_l1tex2xbar_write_sectors_mem_global_op_atom.sum", "l1tex__m_l1tex2xbar_write_sectors_mem_global_op_red.sum",
+    "lts__t_sectors_op_atom.sum", "lts__t_sectors_op_red.sum", "lts__t_sectors_srcunit_tex_op_atom.sum", "lts__t_sectors_srcunit_tex_op_red.sum",
+    "lts__d_atomic_input_cycles_active.avg.pct_of_peak_sustained_elapsed", "lts__d_atomic_input_cycles_active.max.pct_of_peak_sustained_elapsed",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
 ]
 
 
