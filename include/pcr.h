@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PCR_ABI_VERSION 2
+#define PCR_ABI_VERSION 3
 
 /* Point ids stored in the low 32 bits of a visibility key. */
 #define PCR_ID_FLOOR 0xFFFFFFFEu
@@ -98,13 +98,17 @@ typedef struct pcr_style {
     float bounce;        /* weight of the ground-bounce term on spheres (1.0)     */
     int32_t xform;       /* 0: the reference's axis transform (permute, flip, lift);
                             1: none (standardise only) — lets the facade expose
-                            standardize_point_cloud / transform_coordinates separately */
+                            standardize_point_cloud / transform_coordinates separately;
+                            2 (pcr_render_droplet_frames only): the frames are ALREADY standardised
+                            and transformed — used as they are, no statistics taken (the position
+                            colormap has no range then) */
     int32_t mean_mode;   /* how the centre of standardize_point_cloud is summed (PCR_MEAN_*)      */
     /* velocity trails (_add_velocity_trail, traj_ball_renderer.py:98-188): pcr_render_frames[_host] with
      * 6-column frames draws, per point, the straight trail  position - v_hat*L -> position,
      * L = (trail_len_min + (trail_len_max - trail_len_min) * min(|v|/vel_norm, 1)) * camera.trail_scale,
      * as a capsule of radius trail_radius; its id in the visibility buffer is n + point index.   */
-    int32_t trails;          /* 0: none (default), 1: draw them                                   */
+    int32_t trails;          /* 0: none (default), 1: the straight velocity trail, 2 (pcr_render_droplet_frames
+                                only): the Catmull-Rom history trail of traj_renderer.py:204-396           */
     float trail_radius;      /* 0.0007  (traj_ball_renderer.py:160)                               */
     float trail_rgb[3];      /* 0.2, 1.0, 0.4  (:179)                                             */
     double trail_len_min;    /* 0.07 (:132) — doubles: the reference computes the length in f64   */
@@ -253,6 +257,42 @@ int pcr_render_shard(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, i
 int pcr_shade_shard(pcr_ctx* ctx, const uint64_t* d_vis, const void* d_in, int in_is_f64, int64_t n, int cols,
                     const float* d_radius, const float* d_rgb, const double* d_stats10, uint32_t id_base,
                     int owner_only, const pcr_camera* cam, const pcr_style* style, uint8_t* d_rgba, void* stream);
+
+/* ---- droplet scene: traj_renderer.py / traj_vel_renderer.py --------------------------
+ * Those two scripts draw every point as an instance of a droplet mesh (_create_droplet_mesh,
+ * traj_renderer.py:102-153: a surface of revolution of (n_rings+1) x n_segments vertices written to an OBJ
+ * file) placed by the 4x4 matrix of generate_rotation_matrix_from_velocity (:159-202), and one `linearcurve`
+ * polyline per point: the Catmull-Rom history trail of _add_trail_lines (:204-396) or the straight velocity
+ * trail of traj_vel_renderer.py:194-288.  Ids in the visibility buffer: droplet of point i = i, its trail = n + i. */
+#define PCR_HISTORY_FRAMES 20   /* trail_length_frames, traj_renderer.py:218 */
+#define PCR_MAX_CTRL 21         /* 20 spline samples (:272) + the current position (:331) */
+
+/* The mesh: h_verts = HOST [(n_rings+1) * n_segments][3] float32, ring-major, exactly as a loader reads the
+ * OBJ text (6 decimals); faces are the reference's (v0,v2,v1),(v1,v2,v3) per quad.  Ring z must decrease
+ * strictly from ring 0 to ring n_rings.  Synchronous; must be called before pcr_render_droplet_frames. */
+int pcr_set_droplet_mesh(pcr_ctx* ctx, const float* h_verts, int n_rings, int n_segments);
+
+/* generate_rotation_matrix_from_velocity alone: d_pcl = transformed (n, cols) float32; cols == 6: rotation from
+ * the velocity columns; cols == 3: d_rot[n][9] (generate_random_rotation_matrix, :398-418 — the numpy legacy
+ * generator stays on the host) or identity when NULL.  d_xf[n][12] = rows of [R | position], float32 — what a
+ * loader reads from the matrix DROPLET_SEGMENT prints. */
+int pcr_droplet_transforms(pcr_ctx* ctx, const float* d_pcl, int64_t n, int cols, const float* d_rot, float* d_xf, void* stream);
+
+/* _add_trail_lines alone: d_hist = [n_history][n][3] transformed float32 positions of the previous frames
+ * (oldest first; the last 20 are used), d_pos = [n][3] current positions.  d_ctrl[n][PCR_MAX_CTRL][3] = control
+ * points of the curve file the reference writes (after its 6-decimal text round trip), d_count[n] = how many
+ * are valid (0 = the reference draws no trail for that point). */
+int pcr_history_trails(pcr_ctx* ctx, const float* d_hist, int n_history, const float* d_pos, int64_t n, float* d_ctrl,
+                       int32_t* d_count, void* stream);
+
+/* Whole path.  d_in = [n_history + n_frames][n][cols] raw frames on the device: the n_frames frames to render,
+ * preceded by the n_history frames before them (a frame-sharded caller passes a 20-frame halo).  Every frame
+ * is standardised on its own, like the reference's all_frame_data (traj_renderer.py:728-741).  Frame j uses
+ * cams[j]; with style->trails == 2 its history is the up to 20 buffer frames before it; == 1 draws the
+ * velocity trail (cams[j].trail_scale); cols == 3 draws no trails and takes d_rot (or identity). */
+int pcr_render_droplet_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols, int n_frames, int n_history,
+                              const float* d_rot, const pcr_camera* cams, const pcr_style* style, uint64_t* d_vis,
+                              uint8_t* d_rgba, void* stream);
 
 /* Counters of the last pcr_render / pcr_render_frames call (synchronises `stream`):
  * out[0] = kernels launched, out[1] = (tile,sphere) pairs of the last frame,

@@ -8,6 +8,9 @@ What gets pinned:
   trails.npz        tail / head control points of the curve files _add_velocity_trail writes
   scene_*.npz       the scene generate_xml_content emits (centres, radius, reflectance, sensor,
                     floor, emitter), parsed back by oracle/scene_from_xml.py
+  droplets.npz      §8f-2: the droplet OBJ's vertices / faces, the matrices generate_rotation_matrix_from_velocity
+                    and generate_random_rotation_matrix print (as float32), and the control points of the
+                    curve files _add_trail_lines writes for histories of 1..25 frames
   vis_example.npz   visibility ids of the C oracle for the example scene at 200x150 and the
                     sha256 of the full C1 (800x600) key buffer — NOT pinned by the reference
                     (Mitsuba absent): guards the oracle against silent change only.
@@ -34,9 +37,85 @@ def synth(n, cols, seed, dtype):
     return np.ascontiguousarray(a, dtype=dtype)
 
 
+def droplet_inputs(h, n=48, seed=100):
+    """Seeded history of h transformed frames + current positions, with the degenerate cases the reference
+    branches on: points that never move, points that move once and stop, a trail that returns to its start."""
+    rng = np.random.default_rng(seed + h)
+    base = (rng.standard_normal((n, 3)) * 0.3).astype(np.float32)
+    vel = (rng.standard_normal((n, 3)) * 0.02).astype(np.float32)
+    hist = np.stack([(base + vel * np.float32(k) + np.float32(0.001 * k * k)).astype(np.float32) for k in range(h)])
+    pos = (base + vel * np.float32(h) + np.float32(0.001 * h * h)).astype(np.float32)
+    hist[:, :4] = hist[0:1, :4]
+    pos[:3] = hist[0, :3]
+    if h > 2:
+        hist[1:, 5] = hist[1, 5]
+        pos[6] = hist[0, 6]
+    if h > 3:
+        hist[2, 7] = np.nan
+    return hist, pos
+
+
+def gen_droplets(ref):
+    import contextlib
+    import io
+    import tempfile
+    traj = ref["traj_renderer"]
+    g = {}
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                path = traj.TrajectoryRenderer._create_droplet_mesh()
+            V, F = [], []
+            for line in open(path):
+                p = line.split()
+                if p and p[0] == "v":
+                    V.append([float(x) for x in p[1:4]])
+                elif p and p[0] == "f":
+                    F.append([int(x) - 1 for x in p[1:4]])
+            g["mesh_verts"] = np.array(V, np.float64).astype(np.float32)
+            g["mesh_faces"] = np.array(F, np.int32)
+            rng = np.random.default_rng(42)
+            pcl6 = (rng.standard_normal((400, 6)) * [0.3, 0.3, 0.3, 3, 3, 3]).astype(np.float32)
+            pcl6[0, 3:] = 0
+            pcl6[1, 3:] = [0, 0, -2]
+            pcl6[2, 3:] = [0, 0, 3]
+            pcl6[3, 3:] = [1e-9, 0, 5]
+            pcl6[4, 3:] = [0, 1e-7, 0]
+            pcl6[5, 3:] = [1e-7, 0, 0]
+            g["pcl6"] = pcl6
+            g["xf_velocity"] = np.array([traj.TrajectoryRenderer.generate_rotation_matrix_from_velocity(r[3:6], r[:3])
+                                         for r in pcl6]).reshape(-1, 4, 4)[:, :3, :].reshape(-1, 12).astype(np.float32)
+            g["xf_random"] = np.array([traj.TrajectoryRenderer.generate_random_rotation_matrix(i, pcl6[i, :3])
+                                       for i in range(64)]).reshape(-1, 4, 4)[:, :3, :].reshape(-1, 12).astype(np.float32)
+            r = traj.TrajectoryRenderer("x.npy", droplet_mesh_path="m.obj")
+            hs = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15, 17, 19, 20, 25]
+            g["history_lengths"] = np.array(hs)
+            for h in hs:
+                hist, pos = droplet_inputs(h)
+                n = pos.shape[0]
+                ctrl, cnt = np.zeros((n, 21, 3), np.float32), np.zeros(n, np.int32)
+                for i in range(n):
+                    segs = []
+                    r.curve_files = []
+                    r._add_trail_lines(segs, pos[i], np.zeros(3), [hist[k, i] for k in range(h)], point_index=i)
+                    if segs:
+                        rows = np.loadtxt(r.curve_files[-1], ndmin=2)[:, :3].astype(np.float32)
+                        cnt[i] = len(rows)
+                        ctrl[i, :len(rows)] = rows
+                g[f"hist_{h}"], g[f"pos_{h}"], g[f"ctrl_{h}"], g[f"count_{h}"] = hist, pos, ctrl, cnt
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(OUT, "droplets.npz"), **g)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_import.load()
+    if "droplets" in sys.argv[1:]:
+        gen_droplets(ref)
+        return
     ex, ball, orig, b0, b1, traj, vel = (ref[k] for k in ("example_renderer", "traj_ball_renderer", "traj_original",
                                                            "traj_b0", "traj_b1", "traj_renderer", "traj_vel_renderer"))
 
@@ -125,6 +204,8 @@ def main():
         finally:
             os.chdir(cwd)
     np.savez_compressed(os.path.join(OUT, "trails.npz"), **tg)
+
+    gen_droplets(ref)
 
     # ---- oracle self-pin (unpinned by the reference) -----------------------------------------
     pos4 = np.concatenate([sc_ex["centers"], sc_ex["radius"][:, None]], axis=1).astype(np.float32)

@@ -541,6 +541,288 @@ void orc_shade_caps(const uint64_t* vis, const float* cap_a4, const float* cap_b
     }
 }
 
+/* =========================================================================================
+ * Droplet scene of traj_renderer.py / traj_vel_renderer.py: every point is an
+ * instance of the droplet OBJ mesh (_create_droplet_mesh, traj_renderer.py:102-153) placed by the
+ * 4x4 matrix of DROPLET_SEGMENT (:45-55), plus one `linearcurve` polyline per point
+ * (_add_trail_lines :204-396 or _add_velocity_trail, traj_vel_renderer.py:194-288).
+ *
+ * Arithmetic contract "VA-3" (ray-triangle), PARITY UNPINNED against Mitsuba like VA-1:
+ *   world vertex   X_k = fma(M[k][0], vx, fma(M[k][1], vy, fma(M[k][2], vz, M[k][3])))   (M, v binary32)
+ *   camera vertex  to_camera(X)                                   (the sphere-centre transform)
+ *   ray (u,w,1):   e1 = v1-v0, e2 = v2-v0, p = d x e2, det = e1.p, s = -v0, q = s x e1
+ *                  bu = (s.p)/det, bv = (d.q)/det, depth = (e2.q)/det, with 1/det one division;
+ *                  hit iff det != 0, bu >= 0, bv >= 0, bu + bv <= 1, near <= depth <= far.
+ * Every line below is one IEEE binary32 operation; pcr_kernels.cuh:triangle_depth repeats them.
+ * ========================================================================================= */
+static inline int triangle_depth(const float* v0, const float* v1, const float* v2, float u, float w,
+                                 float near_clip, float far_clip, float* depth)
+{
+    const float e1x = v1[0] - v0[0], e1y = v1[1] - v0[1], e1z = v1[2] - v0[2];
+    const float e2x = v2[0] - v0[0], e2y = v2[1] - v0[1], e2z = v2[2] - v0[2];
+    const float px = fmaf(w, e2z, -e2y);
+    const float py = fmaf(-u, e2z, e2x);
+    const float pz = fmaf(u, e2y, -(w * e2x));
+    const float det = fmaf(e1z, pz, fmaf(e1y, py, e1x * px));
+    if (!(det != 0.0f)) return 0;
+    const float inv = 1.0f / det;
+    const float sx = -v0[0], sy = -v0[1], sz = -v0[2];
+    const float bu = fmaf(sz, pz, fmaf(sy, py, sx * px)) * inv;
+    if (!(bu >= 0.0f && bu <= 1.0f)) return 0;
+    const float qx = fmaf(sy, e1z, -(sz * e1y));
+    const float qy = fmaf(sz, e1x, -(sx * e1z));
+    const float qz = fmaf(sx, e1y, -(sy * e1x));
+    const float bv = fmaf(w, qy, fmaf(u, qx, qz)) * inv;
+    if (!(bv >= 0.0f && bu + bv <= 1.0f)) return 0;
+    const float t = fmaf(e2z, qz, fmaf(e2y, qy, e2x * qx)) * inv;
+    if (!(t >= near_clip && t <= far_clip)) return 0;
+    *depth = t;
+    return 1;
+}
+
+/*
+ * Merge n mesh instances into an existing visibility buffer.  verts = nv x 3 (object space, as a
+ * loader reads the OBJ text), faces = nf x 3 zero-based, xf = n x 12 rows [R | t] (binary32).
+ * Instance k gets id id_base + k.  mode 0: every pixel against every triangle of every instance;
+ * mode 1: pixels inside the (padded) screen bbox of the instance's projected vertices only.
+ */
+void orc_visibility_mesh(const float* verts, int32_t nv, const int32_t* faces, int32_t nf, const float* xf, int64_t n,
+                         uint32_t id_base, const orc_frame* f, uint64_t* vis, int mode)
+{
+    const int W = f->W, H = f->H;
+    float* cam = (float*)malloc((size_t)(n > 0 ? n : 1) * (size_t)nv * 3 * sizeof(float));
+    int* box = (int*)malloc((size_t)(n > 0 ? n : 1) * 4 * sizeof(int));
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < n; ++k) {
+        const float* M = xf + 12 * k;
+        float* cv = cam + (size_t)k * nv * 3;
+        int* b = box + 4 * k;
+        float lo_i = 1e30f, hi_i = -1e30f, lo_j = 1e30f, hi_j = -1e30f, zmin = 1e30f, zmax = -1e30f;
+        int finite = 1;
+        for (int v = 0; v < nv; ++v) {
+            const float* o = verts + 3 * v;
+            float X[3];
+            for (int r = 0; r < 3; ++r) X[r] = fmaf(M[4 * r + 0], o[0], fmaf(M[4 * r + 1], o[1], fmaf(M[4 * r + 2], o[2], M[4 * r + 3])));
+            to_camera(f, X, cv + 3 * v);
+            const float* c = cv + 3 * v;
+            if (!(isfinite(c[0]) && isfinite(c[1]) && isfinite(c[2]))) finite = 0;
+            if (c[2] < zmin) zmin = c[2];
+            if (c[2] > zmax) zmax = c[2];
+            if (c[2] > 1e-3f) {
+                float fi = (f->T - c[0] / c[2]) / (2.0f * f->TW) - 0.5f, fj = (f->Th - c[1] / c[2]) / (2.0f * f->TW) - 0.5f;
+                if (fi < lo_i) lo_i = fi;
+                if (fi > hi_i) hi_i = fi;
+                if (fj < lo_j) lo_j = fj;
+                if (fj > hi_j) hi_j = fj;
+            }
+        }
+        if (!finite || zmax < f->near_clip) { b[0] = 1; b[1] = 0; b[2] = 1; b[3] = 0; }
+        else if (mode == 0 || !(zmin > 1e-3f)) { b[0] = 0; b[1] = W - 1; b[2] = 0; b[3] = H - 1; }
+        else {
+            float a0 = ceilf(lo_i - 1.0f), a1 = floorf(hi_i + 1.0f), b0 = ceilf(lo_j - 1.0f), b1 = floorf(hi_j + 1.0f);
+            if (a0 < 0.0f) a0 = 0.0f;
+            if (b0 < 0.0f) b0 = 0.0f;
+            if (a1 > (float)(W - 1)) a1 = (float)(W - 1);
+            if (b1 > (float)(H - 1)) b1 = (float)(H - 1);
+            if (!(a0 <= a1 && b0 <= b1)) { b[0] = 1; b[1] = 0; b[2] = 1; b[3] = 0; }
+            else { b[0] = (int)a0; b[1] = (int)a1; b[2] = (int)b0; b[3] = (int)b1; }
+        }
+    }
+    const int band = 8;
+    const int nb = (H + band - 1) / band;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int bi = 0; bi < nb; ++bi) {
+        int r0 = bi * band, r1 = r0 + band - 1;
+        if (r1 > H - 1) r1 = H - 1;
+        for (int64_t k = 0; k < n; ++k) {
+            const int* b = box + 4 * k;
+            int j0 = b[2] > r0 ? b[2] : r0, j1 = b[3] < r1 ? b[3] : r1;
+            if (j0 > j1 || b[0] > b[1]) continue;
+            const float* cv = cam + (size_t)k * nv * 3;
+            for (int j = j0; j <= j1; ++j) {
+                float w = pix_w(f, j);
+                for (int i = b[0]; i <= b[1]; ++i) {
+                    float u = pix_u(f, i);
+                    uint64_t* dst = vis + (size_t)j * W + i;
+                    for (int t = 0; t < nf; ++t) {
+                        const int32_t* fc = faces + 3 * t;
+                        float d;
+                        if (!triangle_depth(cv + 3 * fc[0], cv + 3 * fc[1], cv + 3 * fc[2], u, w, f->near_clip, f->far_clip, &d)) continue;
+                        uint64_t key = ((uint64_t)f2u(d) << 32) | (uint64_t)(id_base + (uint32_t)k);
+                        if (key < *dst) *dst = key;
+                    }
+                }
+            }
+        }
+    }
+    free(box);
+    free(cam);
+}
+
+/*
+ * Merge n polylines (curve files) into an existing visibility buffer: ctrl = n x max_ctrl x 3 control
+ * points (world space), count[k] of them valid (0 or >= 2); every pair of consecutive control points
+ * is one capsule of the given radius (VA-2); all segments of polyline k share id cap_id_base + k.
+ */
+void orc_visibility_polylines(const float* ctrl, const int32_t* count, int64_t n, int32_t max_ctrl, float radius,
+                              uint32_t cap_id_base, const orc_frame* f, uint64_t* vis, int mode)
+{
+    const int W = f->W, H = f->H;
+    const int ms = max_ctrl - 1;
+    float* cam = (float*)malloc((size_t)(n > 0 ? n : 1) * max_ctrl * 3 * sizeof(float));
+    int* box = (int*)malloc((size_t)(n > 0 ? n : 1) * ms * 4 * sizeof(int));
+    const float r2 = radius * radius;
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < n; ++k) {
+        float* c = cam + (size_t)k * max_ctrl * 3;
+        for (int p = 0; p < count[k]; ++p) to_camera(f, ctrl + ((size_t)k * max_ctrl + p) * 3, c + 3 * p);
+        for (int sg = 0; sg < ms; ++sg) {
+            int* b = box + ((size_t)k * ms + sg) * 4;
+            int ok = sg + 1 < count[k];
+            if (ok && mode == 1) ok = capsule_bbox(f, c + 3 * sg, c + 3 * sg + 3, radius, b, b + 1, b + 2, b + 3);
+            else if (ok) { b[0] = 0; b[1] = W - 1; b[2] = 0; b[3] = H - 1; }
+            if (!ok) { b[0] = 1; b[1] = 0; b[2] = 1; b[3] = 0; }
+        }
+    }
+    const int band = 8;
+    const int nb = (H + band - 1) / band;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int bi = 0; bi < nb; ++bi) {
+        int r0 = bi * band, r1 = r0 + band - 1;
+        if (r1 > H - 1) r1 = H - 1;
+        for (int64_t k = 0; k < n; ++k) {
+            for (int sg = 0; sg + 1 < count[k]; ++sg) {
+                const int* b = box + ((size_t)k * ms + sg) * 4;
+                int j0 = b[2] > r0 ? b[2] : r0, j1 = b[3] < r1 ? b[3] : r1;
+                if (j0 > j1 || b[0] > b[1]) continue;
+                const float* A = cam + ((size_t)k * max_ctrl + sg) * 3;
+                for (int j = j0; j <= j1; ++j) {
+                    float w = pix_w(f, j);
+                    for (int i = b[0]; i <= b[1]; ++i) {
+                        float u = pix_u(f, i);
+                        float vv = fmaf(u, u, fmaf(w, w, 1.0f));
+                        float inv_vv = 1.0f / vv;
+                        float t;
+                        if (!capsule_depth(A, A + 3, r2, u, w, vv, inv_vv, f->near_clip, f->far_clip, &t)) continue;
+                        uint64_t key = ((uint64_t)f2u(t) << 32) | (uint64_t)(cap_id_base + (uint32_t)k);
+                        uint64_t* dst = vis + (size_t)j * W + i;
+                        if (key < *dst) *dst = key;
+                    }
+                }
+            }
+        }
+    }
+    free(box);
+    free(cam);
+}
+
+/* Lit radiance of a diffuse surface point with unit normal nr (the stated look model). */
+static double lit(const double P[3], const double nr[3], const orc_scene* s)
+{
+    const double up[3] = { 0.0, 0.0, 1.0 };
+    double Ld = (double)s->radiance * rect_form_factor(P, nr, s->light_half, s->light_z);
+    double Li = 0.0;
+    if (s->has_floor) {
+        double Pf[3] = { P[0], P[1], (double)s->floor_z };
+        double Bn = (double)s->floor_albedo * (double)s->radiance * rect_form_factor(Pf, up, s->light_half, s->light_z);
+        Li = (double)s->bounce * Bn * 0.5 * (1.0 - nr[2]);
+    }
+    return Ld + Li;
+}
+
+static inline void hit_point(const orc_frame* f, int i, int j, float t, double P[3])
+{
+    float u = pix_u(f, i), w = pix_w(f, j);
+    float dwx = fmaf(w, f->U[0], fmaf(u, f->L[0], f->D[0]));
+    float dwy = fmaf(w, f->U[1], fmaf(u, f->L[1], f->D[1]));
+    float dwz = fmaf(w, f->U[2], fmaf(u, f->L[2], f->D[2]));
+    P[0] = (double)fmaf(t, dwx, f->O[0]); P[1] = (double)fmaf(t, dwy, f->O[1]); P[2] = (double)fmaf(t, dwz, f->O[2]);
+}
+
+/* Overlay the pixels won by polylines: normal = from the nearest point of the nearest segment's axis. */
+void orc_shade_polylines(const uint64_t* vis, const float* ctrl, const int32_t* count, int64_t n, int32_t max_ctrl,
+                         uint32_t cap_id_base, const float trail_rgb[3], const orc_frame* f, const orc_scene* s, uint8_t* rgba)
+{
+    const int W = f->W, H = f->H;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int j = 0; j < H; ++j) {
+        for (int i = 0; i < W; ++i) {
+            uint64_t key = vis[(size_t)j * W + i];
+            uint32_t id = (uint32_t)(key & 0xFFFFFFFFu);
+            if (id < cap_id_base || (int64_t)(id - cap_id_base) >= n || id >= ORC_ID_FLOOR) continue;
+            int64_t k = id - cap_id_base;
+            double P[3];
+            hit_point(f, i, j, u2f((uint32_t)(key >> 32)), P);
+            double best = 1e300, nr[3] = { 0.0, 0.0, 1.0 };
+            for (int sg = 0; sg + 1 < count[k]; ++sg) {
+                const float* A = ctrl + ((size_t)k * max_ctrl + sg) * 3;
+                const float* B = A + 3;
+                double d[3] = { (double)B[0] - A[0], (double)B[1] - A[1], (double)B[2] - A[2] };
+                double dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+                double h = dd > 0.0 ? ((P[0] - A[0]) * d[0] + (P[1] - A[1]) * d[1] + (P[2] - A[2]) * d[2]) / dd : 0.0;
+                if (h < 0.0) h = 0.0;
+                if (h > 1.0) h = 1.0;
+                double q[3] = { P[0] - (A[0] + h * d[0]), P[1] - (A[1] + h * d[1]), P[2] - (A[2] + h * d[2]) };
+                double l2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+                if (l2 < best) { best = l2; nr[0] = q[0]; nr[1] = q[1]; nr[2] = q[2]; }
+            }
+            double l = sqrt(nr[0] * nr[0] + nr[1] * nr[1] + nr[2] * nr[2]);
+            if (l > 0.0) { nr[0] /= l; nr[1] /= l; nr[2] /= l; } else { nr[0] = 0.0; nr[1] = 0.0; nr[2] = 1.0; }
+            double Lo = lit(P, nr, s);
+            uint8_t* px = rgba + ((size_t)j * W + i) * 4;
+            for (int ch = 0; ch < 3; ++ch) px[ch] = srgb8((double)trail_rgb[ch] * Lo);
+            px[3] = 255;
+        }
+    }
+}
+
+/*
+ * Overlay the pixels won by droplet instances (ids id_base .. id_base+n-1).  Shading normal = the smooth
+ * normal of the surface of revolution the mesh samples: prof = (n_rings+1) x 4 rows (ring radius, ring z,
+ * ring normal radial component, ring normal z component) in object space, ring z strictly decreasing; the
+ * hit point is taken to object space, the ring normals either side of its z are interpolated linearly and
+ * swung around the axis to the hit's azimuth.
+ */
+void orc_shade_droplets(const uint64_t* vis, const float* xf, int64_t n, uint32_t id_base, const float* prof, int32_t n_rings,
+                        const float rgb[3], const orc_frame* f, const orc_scene* s, uint8_t* rgba)
+{
+    const int W = f->W, H = f->H;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int j = 0; j < H; ++j) {
+        for (int i = 0; i < W; ++i) {
+            uint64_t key = vis[(size_t)j * W + i];
+            uint32_t id = (uint32_t)(key & 0xFFFFFFFFu);
+            if (id < id_base || (int64_t)(id - id_base) >= n || id >= ORC_ID_FLOOR) continue;
+            const float* M = xf + 12 * (int64_t)(id - id_base);
+            double P[3];
+            hit_point(f, i, j, u2f((uint32_t)(key >> 32)), P);
+            double d[3] = { P[0] - (double)M[3], P[1] - (double)M[7], P[2] - (double)M[11] };
+            double q[3];
+            for (int c = 0; c < 3; ++c) q[c] = (double)M[c] * d[0] + (double)M[4 + c] * d[1] + (double)M[8 + c] * d[2];   /* R^T d */
+            int b = 0;
+            while (b + 1 < n_rings && q[2] < (double)prof[4 * (b + 1) + 1]) ++b;
+            double z0 = prof[4 * b + 1], z1 = prof[4 * (b + 1) + 1];
+            double fr = z0 > z1 ? (z0 - q[2]) / (z0 - z1) : 0.0;
+            if (fr < 0.0) fr = 0.0;
+            if (fr > 1.0) fr = 1.0;
+            double nrr = (double)prof[4 * b + 2] + fr * ((double)prof[4 * (b + 1) + 2] - (double)prof[4 * b + 2]);
+            double nzz = (double)prof[4 * b + 3] + fr * ((double)prof[4 * (b + 1) + 3] - (double)prof[4 * b + 3]);
+            double l = sqrt(nrr * nrr + nzz * nzz);
+            if (l > 0.0) { nrr /= l; nzz /= l; } else { nrr = 1.0; nzz = 0.0; }
+            double rho = sqrt(q[0] * q[0] + q[1] * q[1]);
+            double cx = rho > 1e-12 ? q[0] / rho : 1.0, cy = rho > 1e-12 ? q[1] / rho : 0.0;
+            double no[3] = { nrr * cx, nrr * cy, nzz }, nr[3];
+            for (int c = 0; c < 3; ++c) nr[c] = (double)M[4 * c] * no[0] + (double)M[4 * c + 1] * no[1] + (double)M[4 * c + 2] * no[2];
+            l = sqrt(nr[0] * nr[0] + nr[1] * nr[1] + nr[2] * nr[2]);
+            if (l > 0.0) { nr[0] /= l; nr[1] /= l; nr[2] /= l; } else { nr[0] = 0.0; nr[1] = 0.0; nr[2] = 1.0; }
+            double Lo = lit(P, nr, s);
+            uint8_t* px = rgba + ((size_t)j * W + i) * 4;
+            for (int ch = 0; ch < 3; ++ch) px[ch] = srgb8((double)rgb[ch] * Lo);
+            px[3] = 255;
+        }
+    }
+}
+
 /* torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm of bench.py asks for all cores */
 void orc_set_num_threads(int n)
 {

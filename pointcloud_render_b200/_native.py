@@ -25,7 +25,10 @@ SYMBOLS = (
     "pcr_standardize", "pcr_render", "pcr_shade", "pcr_render_frames", "pcr_render_frames_host",
     "pcr_zmin", "pcr_zmerge_nccl", "pcr_stats_partial", "pcr_standardize_with_stats", "pcr_counters",
     "pcr_transform_coordinates", "pcr_profile", "pcr_profile_read", "pcr_kernel_name", "pcr_set_occlusion", "pcr_finalize_stats", "pcr_velocity_trails", "pcr_render_shard", "pcr_shade_shard",
+    "pcr_set_droplet_mesh", "pcr_droplet_transforms", "pcr_history_trails", "pcr_render_droplet_frames",
 )
+HISTORY_FRAMES, MAX_CTRL = 20, 21                   # PCR_HISTORY_FRAMES, PCR_MAX_CTRL
+TRAILS_NONE, TRAILS_VELOCITY, TRAILS_HISTORY = 0, 1, 2
 
 
 class Camera(ctypes.Structure):
@@ -92,6 +95,10 @@ def load_library():
     L.pcr_render_shard.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp, u32, camp, styp, vp, vp]
     L.pcr_shade_shard.argtypes = [vp, vp, vp, i32, i64, i32, vp, vp, vp, u32, i32, camp, styp, vp, vp]
     L.pcr_velocity_trails.argtypes = [vp, vp, i64, styp, ctypes.c_double, vp, vp, vp, vp]
+    L.pcr_set_droplet_mesh.argtypes = [vp, vp, i32, i32]
+    L.pcr_droplet_transforms.argtypes = [vp, vp, i64, i32, vp, vp, vp]
+    L.pcr_history_trails.argtypes = [vp, vp, i32, vp, i64, vp, vp, vp]
+    L.pcr_render_droplet_frames.argtypes = [vp, vp, i32, i64, i32, i32, i32, vp, camp, styp, vp, vp, vp]
     L.pcr_profile.argtypes = [vp, i32]
     L.pcr_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), i32]
     L.pcr_kernel_name.argtypes = [i32]
@@ -129,7 +136,7 @@ def make_style(color_mode=COLOR_CONST, const_rgb=(0.3, 0.3, 0.3), radius=0.01, f
     s.floor_max = (ctypes.c_float * 2)(*floor_max)
     s.floor_albedo, s.light_z, s.light_half = float(floor_albedo), float(light_z), float(light_half)
     s.radiance, s.bounce, s.xform, s.mean_mode = float(radiance), float(bounce), int(xform), int(mean_mode)
-    s.trails, s.trail_radius = int(bool(trails)), float(trail_radius)
+    s.trails, s.trail_radius = int(trails), float(trail_radius)     # True -> 1 (velocity trail), 2 = history trail
     s.trail_rgb = (ctypes.c_float * 3)(*trail_rgb)
     s.trail_len_min, s.trail_len_max = float(trail_len_min), float(trail_len_max)
     return s
@@ -334,6 +341,53 @@ class Context:
                                                     hp(radius_host), hp(rgb_host), cam_arr, ctypes.byref(style),
                                                     hp(out_vis), hp(rgba)))
         return rgba
+
+    # ---- droplet scene (traj_renderer.py / traj_vel_renderer.py) ---------------------------
+    def set_droplet_mesh(self, verts, n_rings, n_segments):
+        """verts: ((n_rings+1)*n_segments, 3) float32 numpy array, ring-major (the OBJ's vertices)."""
+        v = np.ascontiguousarray(verts, np.float32)
+        assert v.shape == ((n_rings + 1) * n_segments, 3)
+        self._check(self.lib.pcr_set_droplet_mesh(self.handle, v.ctypes.data, int(n_rings), int(n_segments)))
+        self.droplet_mesh = (int(n_rings), int(n_segments))
+
+    def droplet_transforms(self, pcl, rot=None, stream=None):
+        """(N,3|6) float32 CUDA tensor (transformed) [+ rot (N,9) for 3 columns] -> (N,12) rows [R | position]."""
+        import torch
+        assert pcl.is_cuda and pcl.is_contiguous() and pcl.dtype == torch.float32
+        n, cols = pcl.shape
+        xf = torch.empty((n, 12), dtype=torch.float32, device=pcl.device)
+        self._check(self.lib.pcr_droplet_transforms(self.handle, _ptr(pcl), n, cols, _ptr(rot), _ptr(xf), _stream_ptr(stream)))
+        return xf
+
+    def history_trails(self, hist, pos, stream=None):
+        """hist (h,N,3), pos (N,3) float32 CUDA tensors (transformed) -> ctrl (N,21,3) float32, count (N,) int32."""
+        import torch
+        assert pos.is_cuda and pos.is_contiguous() and pos.dtype == torch.float32
+        assert hist.is_contiguous() and hist.dtype == torch.float32
+        n = pos.shape[0]
+        ctrl = torch.zeros((n, MAX_CTRL, 3), dtype=torch.float32, device=pos.device)
+        count = torch.empty(n, dtype=torch.int32, device=pos.device)
+        self._check(self.lib.pcr_history_trails(self.handle, _ptr(hist) if hist.shape[0] else None, int(hist.shape[0]), _ptr(pos), n,
+                                                _ptr(ctrl), _ptr(count), _stream_ptr(stream)))
+        return ctrl, count
+
+    def render_droplet_frames(self, traj, cams, style, n_history=0, rot=None, want_vis=False, out_rgba=None, out_vis=None, stream=None):
+        """traj: (n_history + F, N, 3|6) CUDA tensor — the F frames to render preceded by their history halo;
+        cams: F cameras -> rgba (F,H,W,4) uint8 [, vis (F,H,W) int64]."""
+        import torch
+        assert traj.is_cuda and traj.is_contiguous() and traj.dim() == 3
+        total, n, cols = traj.shape
+        F = total - int(n_history)
+        assert F >= 0 and len(cams) == F
+        W, H = (cams[0].width, cams[0].height) if F else (0, 0)
+        rgba = out_rgba if out_rgba is not None else torch.empty((F, H, W, 4), dtype=torch.uint8, device=traj.device)
+        vis = out_vis if out_vis is not None else (torch.empty((F, H, W), dtype=torch.int64, device=traj.device) if want_vis else None)
+        if F:
+            cam_arr = (Camera * F)(*cams)
+            self._check(self.lib.pcr_render_droplet_frames(self.handle, _ptr(traj), int(traj.dtype == torch.float64), n, cols, F,
+                                                           int(n_history), _ptr(rot), cam_arr, ctypes.byref(style), _ptr(vis), _ptr(rgba),
+                                                           _stream_ptr(stream)))
+        return (rgba, vis) if (want_vis or out_vis is not None) else rgba
 
     # ---- merge ---------------------------------------------------------------------------
     def zmin_(self, dst, src, stream=None):

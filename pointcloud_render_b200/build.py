@@ -13,7 +13,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpcr.so")
 SOURCES = [os.path.join(CSRC, "pcr_api.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "pcr_kernels.cuh"), os.path.join(ROOT, "include", "pcr.h")]
+DEPS = SOURCES + [os.path.join(CSRC, "pcr_kernels.cuh"), os.path.join(CSRC, "pcr_droplets.cuh"), os.path.join(ROOT, "include", "pcr.h")]
 
 
 def nvcc_path():

@@ -3,6 +3,7 @@
 // write_bitmap(sRGB8) chain (example_renderer.py:113-161) with stream-ordered kernel launches.
 #include "pcr.h"
 #include "pcr_kernels.cuh"
+#include "pcr_droplets.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -24,10 +25,12 @@ constexpr int RING_SLOTS = 4;
 constexpr int MAX_STAT_BLOCKS = 1184;   // 148 SMs x 8
 
 enum KernelId { KID_STATS = 0, KID_TRANSFORM, KID_PROJECT, KID_SCAN, KID_SCATTER, KID_RASTER, KID_HIZ, KID_SHADE,
-                KID_ZMIN, KID_AXIS, KID_FILL, KID_MEAN, KID_LUT, KID_COUNT };
+                KID_ZMIN, KID_AXIS, KID_FILL, KID_MEAN, KID_LUT, KID_DROP_PREP, KID_FILL_FLOOR, KID_RASTER_POLY, KID_RASTER_DROP,
+                KID_SHADE_DROP, KID_COUNT };
 const char* const kKernelNames[KID_COUNT] = {"k_stats", "k_transform", "k_project_count", "k_scan_tiles", "k_scatter",
                                              "k_raster_tiles", "k_hiz", "k_shade", "k_zmin", "k_axis_transform",
-                                             "k_fill_tiles", "k_mean_sequential", "k_build_floor_lut"};
+                                             "k_fill_tiles", "k_mean_sequential", "k_build_floor_lut", "k_droplet_prepare",
+                                             "k_fill_floor", "k_raster_polylines", "k_raster_droplets", "k_shade_droplets"};
 constexpr size_t PROF_MAX_RECORDS = 1 << 16;
 
 struct ProfRec { int kid; cudaEvent_t a, b; };
@@ -83,6 +86,19 @@ struct pcr_ctx {
     float *stage_radius = nullptr, *stage_rgb = nullptr;
 
     long long last_overflow_frames = 0;
+
+    // droplet scene (pcr_render_droplet_frames): mesh tables, spline plan, per-frame stats of the whole
+    // buffer, per-point matrices / control points of one batch — all lazily allocated
+    float* mesh_verts = nullptr;
+    float4 *mesh_band = nullptr, *mesh_prof = nullptr;
+    float4 mesh_bound = {0.f, 0.f, 0.f, 0.f};
+    int mesh_rings = 0, mesh_segs = 0;
+    TrailPlan* plan = nullptr;
+    double* dstats = nullptr;
+    size_t dstats_frames = 0;
+    float *dxf = nullptr, *dctrl = nullptr;
+    int* dcount = nullptr;
+    size_t dprep_points = 0;          // capacity of dxf / dctrl / dcount in points (batch * n)
 
     // The scratch is shared by every entry point, so work issued on DIFFERENT streams must not
     // overlap: each entry waits for the previous entry's last event when the stream changed.
@@ -340,7 +356,7 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
     const int raster_ctas = ctx->num_sms * 4;          // k_raster_tiles: 4 CTAs of 256 threads resident per SM (register bound)
     unsigned long long* v = (unsigned long long*)vis;
     // velocity trails (a second primitive per point) only exist in the fused whole-path entry
-    const int trails = raw && st.trails && raw->cols == 6 ? 1 : 0;
+    const int trails = raw && st.trails == 1 && raw->cols == 6 ? 1 : 0;
     if (trails && 2 * (unsigned long long)n > 0xFFFFFFF0ull) return fail(ctx, PCR_ERR_INVALID, "too many points for trail ids (n + i)");
     const uint32_t cap_id_base = trails ? (uint32_t)n : 0u;
     const long long slots = 2 * ctx->max_points;       // survivor slots per frame: sphere + trail per point
@@ -530,7 +546,8 @@ void pcr_destroy(pcr_ctx* ctx)
     cudaDeviceSynchronize();
     void* frees[] = {ctx->surv_count, ctx->ext, ctx->sph, ctx->rect, ctx->partials, ctx->stats, ctx->done, ctx->counts, ctx->offsets,
                      ctx->cursor, ctx->pairs, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
-                     ctx->stage_rgba[0], ctx->stage_rgba[1], ctx->stage_vis[0], ctx->stage_vis[1], ctx->stage_radius, ctx->stage_rgb};
+                     ctx->stage_rgba[0], ctx->stage_rgba[1], ctx->stage_vis[0], ctx->stage_vis[1], ctx->stage_radius, ctx->stage_rgb,
+                     ctx->mesh_verts, ctx->mesh_band, ctx->mesh_prof, ctx->plan, ctx->dstats, ctx->dxf, ctx->dctrl, ctx->dcount};
     for (void* p : frees) if (p) cudaFree(p);
     if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
     for (int k = 0; k < RING_SLOTS; ++k) if (ctx->ring_ev[k]) cudaEventDestroy(ctx->ring_ev[k]);
@@ -955,6 +972,258 @@ int pcr_set_occlusion(pcr_ctx* ctx, int mode, int step, int64_t min_points)
     if (step) ctx->occlusion_step = step;
     if (min_points > 0) ctx->occlusion_min_points = min_points;
     return PCR_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Droplet scene (traj_renderer.py / traj_vel_renderer.py)
+// ------------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+// The reference's sampling plan for a history of h frames (traj_renderer.py:272-316): samples_per_segment =
+// max(2, 20 // (h-1)) samples on every segment, thinned with linspace(0, total-1, 20).astype(int) when that
+// gives more than 20, padded with the last one when fewer.  t, t*t, (t*t)*t are python floats there and meet
+// float32 arrays, so they are rounded to float32 once.
+void build_trail_plan(TrailPlan* plan)
+{
+    memset(plan, 0, sizeof(*plan));
+    for (int k = 0; k < TRAIL_SAMPLES; ++k) {
+        const double t = (double)k / (double)(TRAIL_SAMPLES - 1);
+        plan->s[2][k] = TrailSample{0, (float)t, (float)(1.0 - t), 0.0f};
+    }
+    for (int h = 3; h <= HISTORY_FRAMES; ++h) {
+        const int n_seg = h - 1, sps = std::max(2, TRAIL_SAMPLES / n_seg), total = n_seg * sps;
+        auto sample = [&](int idx) {
+            const int seg = idx / sps, i = idx % sps;
+            const double t = (double)i / (double)(sps - 1);
+            return TrailSample{seg, (float)t, (float)(t * t), (float)((t * t) * t)};
+        };
+        for (int k = 0; k < TRAIL_SAMPLES; ++k) {
+            int idx;
+            if (total > TRAIL_SAMPLES) {
+                const double step = (double)(total - 1) / (double)(TRAIL_SAMPLES - 1);
+                idx = k == TRAIL_SAMPLES - 1 ? total - 1 : (int)((double)k * step);
+            } else {
+                idx = std::min(k, total - 1);
+            }
+            plan->s[h][k] = sample(idx);
+        }
+    }
+}
+
+int ensure_plan(pcr_ctx* ctx)
+{
+    if (ctx->plan) return PCR_OK;
+    TrailPlan* host = new (std::nothrow) TrailPlan;
+    if (!host) return fail(ctx, PCR_ERR_NOMEM, "trail plan");
+    build_trail_plan(host);
+    cudaError_t e = cudaMalloc((void**)&ctx->plan, sizeof(TrailPlan));
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->plan, host, sizeof(TrailPlan), cudaMemcpyHostToDevice);
+    delete host;
+    if (e != cudaSuccess) return fail(ctx, PCR_ERR_CUDA, "trail plan upload", e);
+    return PCR_OK;
+}
+
+DropletMeshDev mesh_dev(const pcr_ctx* ctx)
+{
+    DropletMeshDev m;
+    m.verts = ctx->mesh_verts; m.band = ctx->mesh_band; m.prof = ctx->mesh_prof; m.bound = ctx->mesh_bound;
+    m.n_rings = ctx->mesh_rings; m.n_segs = ctx->mesh_segs; m.nv = (ctx->mesh_rings + 1) * ctx->mesh_segs;
+    return m;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pcr_set_droplet_mesh(pcr_ctx* ctx, const float* h_verts, int n_rings, int n_segments)
+{
+    if (!ctx) return PCR_ERR_INVALID;
+    if (!h_verts || n_rings < 1 || n_rings > DROP_MAX_RINGS || n_segments < 3 || n_segments > DROP_MAX_SEGS ||
+        (n_rings + 1) * n_segments > DROP_MAX_VERTS)
+        return fail(ctx, PCR_ERR_INVALID, "pcr_set_droplet_mesh: bad ring / segment count");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());                       // a previous mesh may still be in use
+    const int nv = (n_rings + 1) * n_segments;
+    // ring profile (vertex 0 of every ring lies in the xz half-plane) and its smooth normals: the normalised
+    // sum of the two adjacent band normals, the poles along the axis (same as oracle/droplet_oracle.py:ring_profile)
+    std::vector<double> pr(n_rings + 1), pz(n_rings + 1), bnr(n_rings), bnz(n_rings);
+    for (int i = 0; i <= n_rings; ++i) { pr[i] = h_verts[(size_t)i * n_segments * 3]; pz[i] = h_verts[(size_t)i * n_segments * 3 + 2]; }
+    for (int i = 0; i < n_rings; ++i) {
+        if (!(pz[i + 1] < pz[i])) return fail(ctx, PCR_ERR_INVALID, "pcr_set_droplet_mesh: ring z must decrease strictly");
+        const double dr = pr[i + 1] - pr[i], dz = pz[i + 1] - pz[i], l = sqrt(dz * dz + dr * dr);
+        bnr[i] = l > 0.0 ? -dz / l : 0.0; bnz[i] = l > 0.0 ? dr / l : 0.0;
+    }
+    std::vector<float4> prof(n_rings + 1), band(n_rings);
+    for (int i = 0; i <= n_rings; ++i) {
+        double nr = 0.0, nz = i == 0 ? 1.0 : -1.0;
+        if (i > 0 && i < n_rings) { nr = bnr[i - 1] + bnr[i]; nz = bnz[i - 1] + bnz[i]; }
+        const double l = sqrt(nr * nr + nz * nz);
+        if (l > 0.0) { nr /= l; nz /= l; }
+        prof[i] = make_float4((float)pr[i], (float)pz[i], (float)nr, (float)nz);
+    }
+    double zlo = 1e300, zhi = -1e300;
+    for (int v = 0; v < nv; ++v) { zlo = std::min(zlo, (double)h_verts[3 * v + 2]); zhi = std::max(zhi, (double)h_verts[3 * v + 2]); }
+    auto radius_about = [&](double zc, int v0, int v1) {
+        double r2 = 0.0;
+        for (int v = v0; v < v1; ++v) {
+            const double x = h_verts[3 * v], y = h_verts[3 * v + 1], z = h_verts[3 * v + 2] - zc;
+            r2 = std::max(r2, x * x + y * y + z * z);
+        }
+        return sqrt(r2);
+    };
+    for (int i = 0; i < n_rings; ++i) {
+        double lo = 1e300, hi = -1e300;
+        for (int v = i * n_segments; v < (i + 2) * n_segments; ++v) { lo = std::min(lo, (double)h_verts[3 * v + 2]); hi = std::max(hi, (double)h_verts[3 * v + 2]); }
+        const double zc = 0.5 * (lo + hi);
+        band[i] = make_float4(0.f, 0.f, (float)zc, (float)radius_about(zc, i * n_segments, (i + 2) * n_segments));
+    }
+    const double zc = 0.5 * (zlo + zhi);
+    ctx->mesh_bound = make_float4(0.f, 0.f, (float)zc, (float)radius_about(zc, 0, nv));
+    for (void* p : {(void*)ctx->mesh_verts, (void*)ctx->mesh_band, (void*)ctx->mesh_prof}) if (p) cudaFree(p);
+    ctx->mesh_verts = nullptr; ctx->mesh_band = nullptr; ctx->mesh_prof = nullptr; ctx->mesh_rings = 0;
+    CK(cudaMalloc((void**)&ctx->mesh_verts, sizeof(float) * 3 * nv));
+    CK(cudaMalloc((void**)&ctx->mesh_band, sizeof(float4) * n_rings));
+    CK(cudaMalloc((void**)&ctx->mesh_prof, sizeof(float4) * (n_rings + 1)));
+    CK(cudaMemcpy(ctx->mesh_verts, h_verts, sizeof(float) * 3 * nv, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->mesh_band, band.data(), sizeof(float4) * n_rings, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->mesh_prof, prof.data(), sizeof(float4) * (n_rings + 1), cudaMemcpyHostToDevice));
+    ctx->mesh_rings = n_rings; ctx->mesh_segs = n_segments;
+    const size_t smem = (size_t)((nv * 3 + 3) & ~3) * sizeof(float) + sizeof(float4) * n_rings;
+    CK(cudaFuncSetAttribute(k_raster_droplets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    return PCR_OK;
+}
+
+int pcr_droplet_transforms(pcr_ctx* ctx, const float* d_pcl, int64_t n, int cols, const float* d_rot, float* d_xf, void* stream)
+{
+    if (!ctx) return PCR_ERR_INVALID;
+    if (n < 0 || (cols != 3 && cols != 6)) return fail(ctx, PCR_ERR_INVALID, "n < 0 or cols not 3|6");
+    if (n == 0) return PCR_OK;
+    if (!d_pcl || !d_xf) return fail(ctx, PCR_ERR_INVALID, "pcr_droplet_transforms: NULL buffer");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    LAUNCH(KID_DROP_PREP, s, k_droplet_transforms<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_pcl, n, cols, d_rot, d_xf));
+    return PCR_OK;
+}
+
+int pcr_history_trails(pcr_ctx* ctx, const float* d_hist, int n_history, const float* d_pos, int64_t n, float* d_ctrl, int32_t* d_count,
+                       void* stream)
+{
+    if (!ctx) return PCR_ERR_INVALID;
+    if (n < 0 || n_history < 0) return fail(ctx, PCR_ERR_INVALID, "pcr_history_trails: negative size");
+    if (n == 0) return PCR_OK;
+    if ((n_history > 0 && !d_hist) || !d_pos || !d_ctrl || !d_count) return fail(ctx, PCR_ERR_INVALID, "pcr_history_trails: NULL buffer");
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_plan(ctx);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    LAUNCH(KID_DROP_PREP, s, k_history_trails<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_hist, n_history, d_pos, n, ctx->plan, d_ctrl, d_count));
+    return PCR_OK;
+}
+
+int pcr_render_droplet_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols, int n_frames, int n_history,
+                              const float* d_rot, const pcr_camera* cams, const pcr_style* style, uint64_t* d_vis, uint8_t* d_rgba,
+                              void* stream)
+{
+    int rc = check_common(ctx, n, cols, style);
+    if (rc) return rc;
+    if (n_frames < 0 || n_history < 0 || !cams || !d_rgba || !d_in) return fail(ctx, PCR_ERR_INVALID, "pcr_render_droplet_frames: NULL buffer");
+    if (n < 1) return fail(ctx, PCR_ERR_INVALID, "pcr_render_droplet_frames: empty frames cannot be standardised");
+    if (!ctx->mesh_rings) return fail(ctx, PCR_ERR_INVALID, "pcr_render_droplet_frames: call pcr_set_droplet_mesh first");
+    if (style->trails < 0 || style->trails > 2) return fail(ctx, PCR_ERR_INVALID, "trails not in {0,1,2}");
+    if (2 * (unsigned long long)n > 0xFFFFFFF0ull) return fail(ctx, PCR_ERR_INVALID, "too many points for trail ids (n + i)");
+    if (n_frames == 0) return PCR_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    StyleDev st = to_style_dev(style);
+    const bool prestandardised = style->xform == 2;       // frames as process() hands them to generate_xml_content
+    if (prestandardised) st.xform = 1;
+    const int W = cams[0].width, H = cams[0].height;
+    for (int f = 0; f < n_frames; ++f)
+        if (cams[f].width != W || cams[f].height != H) return fail(ctx, PCR_ERR_INVALID, "all frames of a call must share W x H");
+    const long long px = (long long)W * H;
+    const size_t elem = in_is_f64 ? 8 : 4;
+    const long long frame_stride = n * cols;
+    const int B = ctx->max_batch;
+    const int total = n_history + n_frames;
+    if (!d_vis) { rc = ensure_vis(ctx); if (rc) return rc; }
+    if ((rc = ensure_plan(ctx))) return rc;
+    if ((rc = enter(ctx, s))) return rc;
+    // scratch that earlier stream-ordered calls may still be reading is only ever grown after a sync
+    const size_t need_pts = (size_t)std::min(B, n_frames) * (size_t)n;
+    if (ctx->dstats_frames < (size_t)total || ctx->dprep_points < need_pts) {
+        CK(cudaDeviceSynchronize());
+        if (ctx->dstats_frames < (size_t)total) {
+            if (ctx->dstats) CK(cudaFree(ctx->dstats));
+            ctx->dstats = nullptr; ctx->dstats_frames = 0;
+            CK(cudaMalloc((void**)&ctx->dstats, sizeof(double) * 10 * (size_t)total));
+            ctx->dstats_frames = (size_t)total;
+        }
+        if (ctx->dprep_points < need_pts) {
+            for (void* p : {(void*)ctx->dxf, (void*)ctx->dctrl, (void*)ctx->dcount}) if (p) CK(cudaFree(p));
+            ctx->dxf = nullptr; ctx->dctrl = nullptr; ctx->dcount = nullptr; ctx->dprep_points = 0;
+            CK(cudaMalloc((void**)&ctx->dxf, sizeof(float) * 12 * need_pts));
+            CK(cudaMalloc((void**)&ctx->dctrl, sizeof(float) * 3 * MAX_CTRL * need_pts));
+            CK(cudaMalloc((void**)&ctx->dcount, sizeof(int) * need_pts));
+            ctx->dprep_points = need_pts;
+        }
+    }
+    // standardisation statistics of every frame in the buffer (the history frames are standardised one by
+    // one, like the reference's all_frame_data, traj_renderer.py:728-741); only the frames actually used
+    const int first_used = st.trails == 2 && cols == 6 ? std::max(0, n_history - HISTORY_FRAMES) : n_history;
+    if (prestandardised)
+        LAUNCH(KID_STATS, s, k_identity_stats<<<(total + 127) / 128, 128, 0, s>>>(ctx->dstats, total));
+    for (int g = first_used; g < total && !prestandardised; g += B) {
+        const int nb = std::min(B, total - g);
+        rc = launch_stats(ctx, (const char*)d_in + (size_t)g * frame_stride * elem, in_is_f64, n, cols, frame_stride, nb, ctx->partials,
+                          ctx->dstats + (size_t)g * 10, 1, s, style->mean_mode);
+        if (rc) return rc;
+    }
+    const DropletMeshDev mesh = mesh_dev(ctx);
+    const size_t smem = (size_t)((mesh.nv * 3 + 3) & ~3) * sizeof(float) + sizeof(float4) * mesh.n_rings;
+    const RawSrc raw = {d_in, in_is_f64, frame_stride, cols, ctx->dstats, nullptr, nullptr};
+    FloorLut lut;
+    if ((rc = floor_lut(ctx, st, s, &lut))) return rc;
+    for (int f0 = 0; f0 < n_frames; f0 += B) {
+        const int nb = std::min(B, n_frames - f0);
+        const int g0 = n_history + f0;
+        rc = upload_frames(ctx, cams + f0, nb, s);
+        if (rc) return rc;
+        unsigned long long* vis = (unsigned long long*)(d_vis ? d_vis + (size_t)f0 * px : ctx->vis);
+        const long long vis_stride = d_vis ? px : (long long)ctx->max_w * ctx->max_h;
+        {
+            dim3 grid((unsigned)((n + 127) / 128), nb);
+            if (in_is_f64)
+                LAUNCH(KID_DROP_PREP, s, k_droplet_prepare<double><<<grid, 128, 0, s>>>(raw_frames<double>(&raw), n, g0, st, ctx->d_frames, d_rot,
+                                                                                      ctx->plan, ctx->dxf, ctx->dctrl, ctx->dcount));
+            else
+                LAUNCH(KID_DROP_PREP, s, k_droplet_prepare<float><<<grid, 128, 0, s>>>(raw_frames<float>(&raw), n, g0, st, ctx->d_frames, d_rot,
+                                                                                     ctx->plan, ctx->dxf, ctx->dctrl, ctx->dcount));
+        }
+        dim3 pgrid((unsigned)((W + 63) / 64), (unsigned)((H + 3) / 4), nb);
+        LAUNCH(KID_FILL_FLOOR, s, k_fill_floor<<<pgrid, 256, 0, s>>>(ctx->d_frames, st, vis, vis_stride));
+        if (st.trails && cols == 6) {
+            dim3 grid((unsigned)((n + 7) / 8), nb);
+            LAUNCH(KID_RASTER_POLY, s, k_raster_polylines<<<grid, 256, 0, s>>>(ctx->d_frames, n, st.trail_radius, (uint32_t)n, ctx->dctrl,
+                                                                              ctx->dcount, vis, vis_stride));
+        }
+        {
+            dim3 grid((unsigned)n, nb);
+            LAUNCH(KID_RASTER_DROP, s, k_raster_droplets<<<grid, 256, smem, s>>>(ctx->d_frames, n, mesh, 0u, ctx->dxf, vis, vis_stride));
+        }
+        uint32_t* rgba = (uint32_t*)(d_rgba + (size_t)f0 * px * 4);
+        if (in_is_f64)
+            LAUNCH(KID_SHADE_DROP, s, k_shade_droplets<double><<<pgrid, 256, 0, s>>>(ctx->d_frames, st, lut, (const uint64_t*)vis, vis_stride,
+                                                                                   raw_frames<double>(&raw), g0, n, mesh, ctx->dxf, ctx->dctrl,
+                                                                                   ctx->dcount, rgba, px));
+        else
+            LAUNCH(KID_SHADE_DROP, s, k_shade_droplets<float><<<pgrid, 256, 0, s>>>(ctx->d_frames, st, lut, (const uint64_t*)vis, vis_stride,
+                                                                                  raw_frames<float>(&raw), g0, n, mesh, ctx->dxf, ctx->dctrl,
+                                                                                  ctx->dcount, rgba, px));
+    }
+    return leave(ctx, s);
 }
 
 const char* pcr_kernel_name(int kernel_id) { return kernel_id >= 0 && kernel_id < KID_COUNT ? kKernelNames[kernel_id] : ""; }

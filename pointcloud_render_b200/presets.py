@@ -87,12 +87,15 @@ class RenderConfig:
                                    trail_scale=self.trail_length_scale(frame_index))
 
     def style(self, color_mode=_native.COLOR_CONST, xform=0, mean_mode=_native.MEAN_AUTO, trails=False):
+        """trails: False / True = the script's velocity trails (when it draws any), 2 = the Catmull-Rom history
+        trails of traj_renderer.py (droplet path only)."""
         return _native.make_style(color_mode=color_mode, const_rgb=self.const_rgb, radius=self.radius,
                                   flip_x=self.flip_x, z_lift=self.z_lift, vel_norm=self.vel_norm, has_floor=True,
                                   floor_z=self.floor_z, floor_min=self.floor_min, floor_max=self.floor_max,
                                   floor_albedo=self.floor_albedo, light_z=self.light_z, light_half=self.light_half,
                                   radiance=self.radiance, bounce=self.bounce, xform=xform, mean_mode=mean_mode,
-                                  trails=trails and self.trail_schedule is not None, trail_radius=self.trail_radius,
+                                  trails=(2 if trails == 2 else int(bool(trails) and self.trail_schedule is not None)),
+                                  trail_radius=self.trail_radius,
                                   trail_rgb=self.trail_rgb, trail_len_min=self.trail_len_min, trail_len_max=self.trail_len_max)
 
     def for_trajectory(self, n_frames):

@@ -7,8 +7,8 @@ Same class and method names, argument meaning and error behaviour as the referen
   FixedFrame199Renderer     traj_original.py:6-142   (no x flip, fixed camera)
   TrajB0Renderer            traj_b0.py:6-191         (class is also called FixedFrame199Renderer there)
   TrajB1Renderer            traj_b1.py:6-191
-  TrajectoryRenderer        traj_renderer.py:87-676  (points drawn as spheres — droplet mesh and
-  TrajectoryVelRenderer     traj_vel_renderer.py:80-530  trails are SURVEY.md §8f "next" rows)
+  TrajectoryRenderer        traj_renderer.py:87-676      (droplet meshes + Catmull-Rom history trails)
+  TrajectoryVelRenderer     traj_vel_renderer.py:80-530  (droplet meshes + straight velocity trails)
 
 What changes is the seam: `render_scene` takes the transformed point array
 instead of an XML path, and nothing is written to disk between the stages — centres, radii and
@@ -309,16 +309,163 @@ class TrajB1Renderer(TrajectoryBallRenderer):
     PRESET = "traj_b1"
 
 
-class TrajectoryRenderer(TrajectoryBallRenderer):
-    """traj_renderer.py:87 — linear dolly camera (:519-527), 256 spp scene; points as spheres."""
+class _DropletMixin:
+    """What traj_renderer.py and traj_vel_renderer.py share: every point is an instance of the droplet mesh
+    (_create_droplet_mesh, traj_renderer.py:102-153) oriented along its velocity, plus one trail curve.
+    TRAILS: 1 = straight velocity trail (traj_vel_renderer.py:194-288), 2 = Catmull-Rom history trail
+    (traj_renderer.py:204-396).  droplets=False in the constructor keeps the sphere path of the parent."""
+    TRAILS = _native.TRAILS_NONE
+
+    def __init__(self, file_path, output_folder=None, droplet_mesh_path=None, droplets=True, **kw):
+        # droplet_mesh_path: the reference lets a caller substitute an OBJ file; the mesh here is the built-in
+        # surface of revolution (there is no file), so the argument is accepted and ignored
+        super().__init__(file_path, output_folder=output_folder, **kw)
+        self.droplets = bool(droplets)
+        self.droplet_mesh_path = droplet_mesh_path
+        self.curve_files = []           # the reference's temp curve files: none are written any more
+
+    @staticmethod
+    def _create_droplet_mesh():
+        """traj_renderer.py:102-153 without the OBJ file: ((17*20), 3) float32 vertices, (640, 3) faces."""
+        from . import droplets
+        return droplets.droplet_vertices(), droplets.droplet_faces()
+
+    @classmethod
+    def generate_rotation_matrix_from_velocity(cls, velocity, translation):
+        """traj_renderer.py:159-202 on the device: flattened 4x4 (float32 values, what a loader reads
+        from the matrix the reference prints)."""
+        import torch
+        row = torch.tensor([[*map(float, translation), *map(float, velocity)]], dtype=torch.float32, device=f"cuda:{cls.DEVICE}")
+        xf = _engine(cls.DEVICE, 1, 16, 16).droplet_transforms(row).cpu().numpy().reshape(3, 4).astype(np.float64)
+        return np.concatenate([xf, [[0.0, 0.0, 0.0, 1.0]]]).flatten()
+
+    @staticmethod
+    def generate_random_rotation_matrix(seed, translation):
+        """traj_renderer.py:398-418 (numpy's legacy generator stays on the host)."""
+        from . import droplets
+        m = np.eye(4)
+        m[:3, :3] = droplets.random_rotations(int(seed) + 1)[int(seed)].reshape(3, 3)
+        m[:3, 3] = translation
+        return m.flatten()
+
+    def _droplet_engine(self, n, batch=1):
+        from . import droplets
+        eng = _engine(self.DEVICE, n, self.width, self.height, batch=batch)
+        if getattr(eng, "droplet_mesh", None) != (droplets.N_RINGS, droplets.N_SEGMENTS):
+            eng.set_droplet_mesh(droplets.droplet_vertices(), droplets.N_RINGS, droplets.N_SEGMENTS)
+        return eng
+
+    def _rotations(self, n, cols, device):
+        """Rotations of points without velocity: random per index for traj_renderer.py (:566),
+        identity for traj_vel_renderer.py (:427-430)."""
+        import torch
+        if cols == 6 or self.TRAILS != _native.TRAILS_HISTORY:
+            return None
+        from . import droplets
+        return torch.from_numpy(np.ascontiguousarray(droplets.random_rotations(n))).to(device)
+
+    def render_scene(self, pcl, frame_index=0, total_frames=220, history_pcls=None):
+        """generate_xml_content + mi.load_file + mi.render of the droplet scripts (traj_renderer.py:529-602):
+        `pcl` and `history_pcls` are standardised, transformed (N,3|6) arrays, history oldest first."""
+        import torch
+        if not self.droplets:
+            return super().render_scene(pcl, frame_index=frame_index, total_frames=total_frames)
+        t, _ = _to_device(pcl, self.DEVICE)
+        t = t.to(torch.float32)
+        n, cols = t.shape
+        hist = []
+        if self.TRAILS == _native.TRAILS_HISTORY and cols == 6 and history_pcls:
+            for h in list(history_pcls)[-_native.HISTORY_FRAMES:]:
+                h, _ = _to_device(h, self.DEVICE)
+                h = h.to(torch.float32)
+                if h.shape[0] < n:                       # the reference skips points a history frame lacks
+                    raise ValueError("history frames must hold every point of the current frame")
+                hh = torch.zeros((n, cols), dtype=torch.float32, device=t.device)
+                hh[:, :3] = h[:n, :3]
+                hist.append(hh)
+        buf = torch.stack(hist + [t]).contiguous()
+        eng = self._droplet_engine(n)
+        style = self.config.style(color_mode=self.color_mode, xform=2, trails=self.TRAILS if self.trails else 0)
+        cam = self.config.camera(frame_index, total_frames, self.width, self.height)
+        rgba, vis = eng.render_droplet_frames(buf, [cam], style, n_history=len(hist), rot=self._rotations(n, cols, t.device), want_vis=True)
+        return RenderedScene(rgba[0], vis[0])
+
+    def render_trajectory(self, traj, first_frame=0, total_frames=None, want_vis=False, max_batch=16, stretch=True, out_rgba=None,
+                          n_history=0):
+        """traj: (n_history + F, N, 3|6) raw frames — the F frames to render preceded by n_history frames of
+        history (a frame-sharded caller passes a 20-frame halo; rank 0 passes 0).  Whole path in one call:
+        pcr_render_droplet_frames.  Frame f of the F uses compute_camera_position(first_frame + f)."""
+        import torch
+        if not self.droplets:
+            return super().render_trajectory(traj, first_frame, total_frames, want_vis, max_batch, stretch, out_rgba)
+        t = traj if isinstance(traj, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(traj))
+        was_cuda = t.is_cuda
+        total, n, cols = t.shape
+        F = total - int(n_history)
+        tot = int(total_frames or (first_frame + F))
+        cfg = self.config.for_trajectory(tot) if stretch else self.config
+        cams = [cfg.camera(first_frame + f, tot, self.width, self.height) for f in range(F)]
+        style = self.config.style(color_mode=self.color_mode, trails=self.TRAILS if self.trails else 0)
+        eng = self._droplet_engine(n, batch=min(max_batch, max(F, 1)))
+        dev = t.to(f"cuda:{self.DEVICE}", non_blocking=True).contiguous()
+        out = eng.render_droplet_frames(dev, cams, style, n_history=int(n_history), rot=self._rotations(n, cols, dev.device),
+                                        want_vis=want_vis, out_rgba=out_rgba if (out_rgba is not None and out_rgba.is_cuda) else None)
+        rgba, vis = out if want_vis else (out, None)
+        if not was_cuda:
+            if out_rgba is not None and not out_rgba.is_cuda:
+                out_rgba.copy_(rgba)
+                rgba = out_rgba
+            else:
+                rgba = rgba.cpu()
+            vis = None if vis is None else vis.cpu()
+        return (rgba, vis) if want_vis else rgba
+
+
+class TrajectoryRenderer(_DropletMixin, TrajectoryBallRenderer):
+    """traj_renderer.py:87 — droplets + Catmull-Rom history trails, linear dolly camera (:519-527)."""
     PRESET = "traj"
+    TRAILS = _native.TRAILS_HISTORY
+
+    def __init__(self, file_path, output_folder=None, droplet_mesh_path=None, droplets=True, trails=True, **kw):
+        super().__init__(file_path, output_folder=output_folder, droplet_mesh_path=droplet_mesh_path, droplets=droplets, trails=trails, **kw)
 
     def process(self, frame_index=0, history_pcls=None, total_frames=220):
-        # history_pcls feeds the Catmull-Rom trails (traj_renderer.py:204-396): §8f-2, accepted and unused
-        return super().process(frame_index=frame_index, total_frames=total_frames)
+        """traj_renderer.py:604-646: history_pcls = the previous (<= 20) frames, standardised and transformed."""
+        pcl = self.load_point_cloud()
+        if len(pcl.shape) == 3:
+            pcl = pcl[0]
+        pcl, _ = _to_device(pcl, self.DEVICE)
+        pcl = self.standardize_point_cloud(pcl)
+        pcl = self.transform_coordinates(pcl)
+        output_filename = f'frame_{frame_index:04d}_b0' if frame_index > 199 else self.filename
+        output_file_path = self._output_path(output_filename)
+        print('  Rendering...', end=' ', flush=True)
+        rendered_scene = self.render_scene(pcl, frame_index=frame_index, total_frames=total_frames, history_pcls=history_pcls)
+        print('Saving...', end=' ', flush=True)
+        self.save_scene(output_file_path, rendered_scene)
+        print('Done!')
+
+    @staticmethod
+    def cleanup_temp_meshes():
+        """traj_renderer.py:648-653: nothing to clean — no temp_meshes/ directory is created."""
+
+    def cleanup_temp_curves(self):
+        self.curve_files = []
+
+    @staticmethod
+    def cleanup_temp_curves_dir():
+        """traj_renderer.py:666-671: nothing to clean — no temp_curves/ directory is created."""
 
 
-class TrajectoryVelRenderer(TrajectoryBallRenderer):
-    """traj_vel_renderer.py:80 — camera as traj_ball (:381-407); velocity attribute available to
-    the colour hook (PCR_COLOR_VELOCITY)."""
+class TrajectoryVelRenderer(_DropletMixin, TrajectoryBallRenderer):
+    """traj_vel_renderer.py:80 — droplets + straight velocity trails (:194-288), camera as traj_ball (:381-407);
+    velocity attribute available to the colour hook (PCR_COLOR_VELOCITY)."""
     PRESET = "traj_vel"
+    TRAILS = _native.TRAILS_VELOCITY
+
+    def __init__(self, file_path, output_folder=None, droplet_mesh_path=None, droplets=True, trails=True, **kw):
+        super().__init__(file_path, output_folder=output_folder, droplet_mesh_path=droplet_mesh_path, droplets=droplets, trails=trails, **kw)
+
+    cleanup_temp_meshes = TrajectoryRenderer.cleanup_temp_meshes
+    cleanup_temp_curves = TrajectoryRenderer.cleanup_temp_curves
+    cleanup_temp_curves_dir = TrajectoryRenderer.cleanup_temp_curves_dir
