@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="H", choices=["H", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--workload", default="H", choices=["H", "C2", "C3", "C4", "C5", "C2D", "C4D"])
     ap.add_argument("--points", type=int, default=0, help="override the workload's point count (C5 scaling studies)")
     ap.add_argument("--frames-per-step", type=int, default=0, help="frames per step per GPU (0 = workload default)")
     ap.add_argument("--ring", type=int, default=0, help="resident frames per GPU (0 = enough to exceed L2)")
@@ -55,7 +55,7 @@ def parse_args():
 def workload_spec(name, frames_per_step):
     from pointcloud_render_b200 import synthetic
     c = dict(synthetic.CONFIGS[name])
-    default_fps = {"H": 16, "C4": 64, "C3": 64, "C2": 64, "C5": 1}[name]
+    default_fps = {"H": 16, "C4": 64, "C3": 64, "C2": 64, "C5": 1, "C2D": 16, "C4D": 8}[name]
     c["frames_per_step"] = frames_per_step or default_fps
     b_in = 4 * c["cols"] + (4 if c["radii"] else 0)
     # input read once, u64 visibility written once, RGBA8 written once
@@ -363,6 +363,138 @@ def run_point_sharded(args, spec, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def moving_trajectory(frames, n, seed, dt=0.01):
+    """(frames, n, 6) ballistic trajectory whose velocities are independent of the positions (synthetic.trajectory
+    draws V = 3 P0, a pure expansion that the per-frame standardisation removes: no history trail would show)."""
+    rng = np.random.default_rng(seed)
+    p0, v, g = rng.standard_normal((n, 3)), 3.0 * rng.standard_normal((n, 3)), np.array([0.0, -1.0, 0.0])
+    out = np.empty((frames, n, 6), np.float32)
+    for f in range(frames):
+        t = f * dt
+        out[f, :, :3] = p0 + t * v + 0.5 * t * t * g
+        out[f, :, 3:] = v + t * g
+    return out
+
+
+def run_droplets(args, spec, rank, world, local_rank):
+    """C2D / C4D: the droplet scene of traj_renderer.py (history trails) / traj_vel_renderer.py (velocity trails)
+    through pcr_render_droplet_frames.  A step renders frames_per_step frames that have a full 20-frame history."""
+    import torch
+    from oracle import droplet_oracle as do, pcr_oracle as orc
+    from pointcloud_render_b200 import _native, droplets
+    from pointcloud_render_b200.presets import PRESETS
+    torch.cuda.set_device(local_rank)
+    B, n, W, H = spec["frames_per_step"], spec["points"], spec["width"], spec["height"]
+    trails = spec["droplet_trails"]
+    cfg = PRESETS[spec["preset"]].for_trajectory(spec["frames"])
+    halo = 20 if trails == 2 else 0
+    host_np = moving_trajectory(halo + 2 * B, n, seed=rank)
+    host = torch.from_numpy(host_np).pin_memory()
+    resident = host.cuda()
+    ctx = _native.Context(device=local_rank, max_points=n, max_w=W, max_h=H, max_batch=min(B, 16))
+    ctx.set_droplet_mesh(droplets.droplet_vertices(), droplets.N_RINGS, droplets.N_SEGMENTS)
+    style = cfg.style(color_mode=0, trails=trails if trails == 2 else True)
+    first = spec["frames"] // 2
+    cams = [cfg.camera(first + k, spec["frames"], W, H) for k in range(2 * B)]
+    rgba = torch.empty((B, H, W, 4), dtype=torch.uint8, device="cuda")
+    host_rgba = torch.empty((B, H, W, 4), dtype=torch.uint8).pin_memory()
+
+    def step_device(s):
+        k = (s % 2) * B
+        ctx.render_droplet_frames(resident[k:k + halo + B], cams[k:k + B], style, n_history=halo, out_rgba=rgba)
+
+    def step_host(s):
+        k = (s % 2) * B
+        dev = host[k:k + halo + B].cuda(non_blocking=True)
+        ctx.render_droplet_frames(dev, cams[k:k + B], style, n_history=halo, out_rgba=rgba)
+        host_rgba.copy_(rgba, non_blocking=True)
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    for s in range(args.warmup):
+        step_device(s)
+    torch.cuda.synchronize()
+    ctx.profile_read()
+    ctx.profile(True)
+    launches0 = ctx.counters()["launches"]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.begin()
+    ev0.record()
+    for s in range(args.steps):
+        step_device(args.warmup + s)
+    ev1.record()
+    torch.cuda.synchronize()
+    dev_ms = ev0.elapsed_time(ev1)
+    ctx.profile(False)
+    prof = ctx.profile_read()
+    launches = ctx.counters()["launches"] - launches0
+    fps = B * args.steps / (dev_ms * 1e-3)
+    for s in range(2):
+        step_host(s)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step_host(s)
+    e2e_s = time.perf_counter() - t0
+    sampler.end()
+    sampler.stop()
+    total_ms = sum(v[0] for v in prof.values())
+    kernels = {k: {"ms_total": round(v[0], 4), "launches": int(v[1]), "us_per_launch": round(v[0] / v[1] * 1e3, 3), "share": round(v[0] / total_ms, 4)}
+               for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+    top = max(prof.items(), key=lambda kv: kv[1][0])
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.isfile(peaks_path) else 6650.0
+    frames_per_launch = min(B, ctx.max_batch)
+    bytes_per_launch = spec["algorithmic_bytes_per_frame"] * frames_per_launch
+    achieved = bytes_per_launch / (top[1][0] / top[1][1] * 1e-3) / 1e9
+    # CPU side: the oracle's droplet scene for a few frames (numpy geometry + OpenMP C mesh / polyline caster + shading)
+    orc.set_num_threads()
+    t_cpu, frames_cpu = 0.0, 0
+    sc = orc.make_scene(True, cfg.floor_z, cfg.floor_min, cfg.floor_max, cfg.floor_albedo, cfg.light_z, cfg.light_half, cfg.radiance, cfg.bounce)
+    while frames_cpu < 6 and t_cpu < 20.0 and not args.no_cpu_baseline:
+        f = halo + frames_cpu
+        t0 = time.perf_counter()
+        std = [orc.transform_coordinates(orc.standardize_point_cloud(host_np[k]), cfg.flip_x) for k in range(f - halo, f + 1)]
+        pcl = std[-1]
+        xf = do.to_world_f32(do.rotation_from_velocity(pcl[:, 3:6]), pcl[:, :3])
+        if trails == 2:
+            ctrl, count = do.history_trails(np.stack([x[:, :3] for x in std[:-1]]), pcl[:, :3])
+        else:
+            tail, head, valid = orc.velocity_trails(pcl, cfg.trail_length_scale(first + frames_cpu))
+            ctrl = np.zeros((n, 21, 3), np.float32)
+            ctrl[:, 0], ctrl[:, 1] = tail, head
+            count = np.where(valid, 2, 0).astype(np.int32)
+        fr = orc.camera_frame(cfg.camera_position(first + frames_cpu, spec["frames"]), cfg.target, cfg.up, cfg.fov, cfg.near_clip, cfg.far_clip, W, H)
+        vis = do.add_droplets(do.add_polylines(orc.visibility(np.zeros((0, 4), np.float32), fr, sc), ctrl, count, fr, n, radius=cfg.trail_radius), xf, fr)
+        do.shade_droplet_scene(vis, xf, ctrl, count, fr, sc)
+        t_cpu += time.perf_counter() - t0
+        frames_cpu += 1
+    line = {"metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "mpoints_per_s": fps * n / 1e6,
+            "config": {"workload": f"{args.workload}: droplet scene, {n} points/frame (6 cols f32), {W}x{H}, preset {spec['preset']}, "
+                                   + ("Catmull-Rom history trails over a 20-frame halo" if trails == 2 else "straight velocity trails"),
+                       "points": n, "width": W, "height": H, "frames_per_step_per_gpu": B,
+                       "l2_policy": f"outputs larger than L2: every step rewrites {B * W * H * 12 / 1e6:.0f} MB of keys + images; the inputs "
+                                    f"({(halo + B) * n * 24 / 1e6:.1f} MB per step) are far smaller than L2 and alternate between two windows",
+                       "parallelism": "single GPU"},
+            "e2e": {"value": B * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int((halo + B) * n * 24),
+                    "d2h_bytes_per_step": int(B * W * H * 4), "ms_per_step": e2e_s / args.steps * 1e3,
+                    "api": "pinned host trajectory window -> device, pcr_render_droplet_frames, RGBA8 -> pinned host"},
+            "gpu_launches": int(launches), "kernels": kernels,
+            "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "algorithmic_bytes_per_launch": bytes_per_launch, "frames_per_launch": frames_per_launch,
+                         "us_per_launch": top[1][0] / top[1][1] * 1e3,
+                         "note": "algorithmic bytes = N*24 + W*H*(8+4) per frame; the droplet raster is bound by ray-triangle tests, not HBM"},
+            "clocks": sampler.summary()}
+    if frames_cpu:
+        line["cpu_baseline"] = {"value": frames_cpu / t_cpu, "unit": "frames/s", "cores": orc.num_threads(), "kind": "port",
+                                "sample": f"{frames_cpu} frames of the same workload ({t_cpu:.1f} s): numpy standardise / rotations / Catmull-Rom "
+                                          "(per-point python loop for the trail de-duplication), OpenMP C mesh + polyline caster, shading",
+                                "host_cpus": os.cpu_count()}
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -371,6 +503,11 @@ def main():
     spec = workload_spec(args.workload, args.frames_per_step)
     if args.points:
         spec["points"] = args.points
+    if args.workload in ("C2D", "C4D"):
+        if args.impl == "reference" or world > 1:
+            raise SystemExit("the droplet workloads are single-GPU device arms (--impl ours, --gpus 1)")
+        run_droplets(args, spec, rank, world, local_rank)
+        return
     if args.workload == "C5" and args.impl == "ours":
         run_point_sharded(args, spec, rank, world, local_rank)
         return

@@ -90,7 +90,7 @@ struct pcr_ctx {
     // droplet scene (pcr_render_droplet_frames): mesh tables, spline plan, per-frame stats of the whole
     // buffer, per-point matrices / control points of one batch — all lazily allocated
     float* mesh_verts = nullptr;
-    float4 *mesh_band = nullptr, *mesh_prof = nullptr;
+    float4* mesh_prof = nullptr;
     float4 mesh_bound = {0.f, 0.f, 0.f, 0.f};
     int mesh_rings = 0, mesh_segs = 0;
     TrailPlan* plan = nullptr;
@@ -547,7 +547,7 @@ void pcr_destroy(pcr_ctx* ctx)
     void* frees[] = {ctx->surv_count, ctx->ext, ctx->sph, ctx->rect, ctx->partials, ctx->stats, ctx->done, ctx->counts, ctx->offsets,
                      ctx->cursor, ctx->pairs, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
                      ctx->stage_rgba[0], ctx->stage_rgba[1], ctx->stage_vis[0], ctx->stage_vis[1], ctx->stage_radius, ctx->stage_rgb,
-                     ctx->mesh_verts, ctx->mesh_band, ctx->mesh_prof, ctx->plan, ctx->dstats, ctx->dxf, ctx->dctrl, ctx->dcount};
+                     ctx->mesh_verts, ctx->mesh_prof, ctx->plan, ctx->dstats, ctx->dxf, ctx->dctrl, ctx->dcount};
     for (void* p : frees) if (p) cudaFree(p);
     if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
     for (int k = 0; k < RING_SLOTS; ++k) if (ctx->ring_ev[k]) cudaEventDestroy(ctx->ring_ev[k]);
@@ -1029,7 +1029,7 @@ int ensure_plan(pcr_ctx* ctx)
 DropletMeshDev mesh_dev(const pcr_ctx* ctx)
 {
     DropletMeshDev m;
-    m.verts = ctx->mesh_verts; m.band = ctx->mesh_band; m.prof = ctx->mesh_prof; m.bound = ctx->mesh_bound;
+    m.verts = ctx->mesh_verts; m.prof = ctx->mesh_prof; m.bound = ctx->mesh_bound;
     m.n_rings = ctx->mesh_rings; m.n_segs = ctx->mesh_segs; m.nv = (ctx->mesh_rings + 1) * ctx->mesh_segs;
     return m;
 }
@@ -1056,7 +1056,7 @@ int pcr_set_droplet_mesh(pcr_ctx* ctx, const float* h_verts, int n_rings, int n_
         const double dr = pr[i + 1] - pr[i], dz = pz[i + 1] - pz[i], l = sqrt(dz * dz + dr * dr);
         bnr[i] = l > 0.0 ? -dz / l : 0.0; bnz[i] = l > 0.0 ? dr / l : 0.0;
     }
-    std::vector<float4> prof(n_rings + 1), band(n_rings);
+    std::vector<float4> prof(n_rings + 1);
     for (int i = 0; i <= n_rings; ++i) {
         double nr = 0.0, nz = i == 0 ? 1.0 : -1.0;
         if (i > 0 && i < n_rings) { nr = bnr[i - 1] + bnr[i]; nz = bnz[i - 1] + bnz[i]; }
@@ -1064,35 +1064,22 @@ int pcr_set_droplet_mesh(pcr_ctx* ctx, const float* h_verts, int n_rings, int n_
         if (l > 0.0) { nr /= l; nz /= l; }
         prof[i] = make_float4((float)pr[i], (float)pz[i], (float)nr, (float)nz);
     }
-    double zlo = 1e300, zhi = -1e300;
+    double zlo = 1e300, zhi = -1e300, r2 = 0.0;
     for (int v = 0; v < nv; ++v) { zlo = std::min(zlo, (double)h_verts[3 * v + 2]); zhi = std::max(zhi, (double)h_verts[3 * v + 2]); }
-    auto radius_about = [&](double zc, int v0, int v1) {
-        double r2 = 0.0;
-        for (int v = v0; v < v1; ++v) {
-            const double x = h_verts[3 * v], y = h_verts[3 * v + 1], z = h_verts[3 * v + 2] - zc;
-            r2 = std::max(r2, x * x + y * y + z * z);
-        }
-        return sqrt(r2);
-    };
-    for (int i = 0; i < n_rings; ++i) {
-        double lo = 1e300, hi = -1e300;
-        for (int v = i * n_segments; v < (i + 2) * n_segments; ++v) { lo = std::min(lo, (double)h_verts[3 * v + 2]); hi = std::max(hi, (double)h_verts[3 * v + 2]); }
-        const double zc = 0.5 * (lo + hi);
-        band[i] = make_float4(0.f, 0.f, (float)zc, (float)radius_about(zc, i * n_segments, (i + 2) * n_segments));
-    }
     const double zc = 0.5 * (zlo + zhi);
-    ctx->mesh_bound = make_float4(0.f, 0.f, (float)zc, (float)radius_about(zc, 0, nv));
-    for (void* p : {(void*)ctx->mesh_verts, (void*)ctx->mesh_band, (void*)ctx->mesh_prof}) if (p) cudaFree(p);
-    ctx->mesh_verts = nullptr; ctx->mesh_band = nullptr; ctx->mesh_prof = nullptr; ctx->mesh_rings = 0;
+    for (int v = 0; v < nv; ++v) {
+        const double x = h_verts[3 * v], y = h_verts[3 * v + 1], z = h_verts[3 * v + 2] - zc;
+        r2 = std::max(r2, x * x + y * y + z * z);
+    }
+    ctx->mesh_bound = make_float4(0.f, 0.f, (float)zc, (float)sqrt(r2));
+    for (void* p : {(void*)ctx->mesh_verts, (void*)ctx->mesh_prof}) if (p) cudaFree(p);
+    ctx->mesh_verts = nullptr; ctx->mesh_prof = nullptr; ctx->mesh_rings = 0;
     CK(cudaMalloc((void**)&ctx->mesh_verts, sizeof(float) * 3 * nv));
-    CK(cudaMalloc((void**)&ctx->mesh_band, sizeof(float4) * n_rings));
     CK(cudaMalloc((void**)&ctx->mesh_prof, sizeof(float4) * (n_rings + 1)));
     CK(cudaMemcpy(ctx->mesh_verts, h_verts, sizeof(float) * 3 * nv, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->mesh_band, band.data(), sizeof(float4) * n_rings, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->mesh_prof, prof.data(), sizeof(float4) * (n_rings + 1), cudaMemcpyHostToDevice));
     ctx->mesh_rings = n_rings; ctx->mesh_segs = n_segments;
-    const size_t smem = (size_t)((nv * 3 + 3) & ~3) * sizeof(float) + sizeof(float4) * n_rings;
-    CK(cudaFuncSetAttribute(k_raster_droplets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    CK(cudaFuncSetAttribute(k_raster_droplets, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
     return PCR_OK;
 }
 
@@ -1182,7 +1169,9 @@ int pcr_render_droplet_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int
         if (rc) return rc;
     }
     const DropletMeshDev mesh = mesh_dev(ctx);
-    const size_t smem = (size_t)((mesh.nv * 3 + 3) & ~3) * sizeof(float) + sizeof(float4) * mesh.n_rings;
+    // one warp per droplet; as many warps per CTA as the camera-space vertices of their instances fit in shared memory
+    const int drop_warps = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)ctx->smem_optin / ((size_t)mesh.nv * 12)));
+    const size_t smem = (size_t)drop_warps * mesh.nv * 12;
     const RawSrc raw = {d_in, in_is_f64, frame_stride, cols, ctx->dstats, nullptr, nullptr};
     FloorLut lut;
     if ((rc = floor_lut(ctx, st, s, &lut))) return rc;
@@ -1210,8 +1199,8 @@ int pcr_render_droplet_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int
                                                                               ctx->dcount, vis, vis_stride));
         }
         {
-            dim3 grid((unsigned)n, nb);
-            LAUNCH(KID_RASTER_DROP, s, k_raster_droplets<<<grid, 256, smem, s>>>(ctx->d_frames, n, mesh, 0u, ctx->dxf, vis, vis_stride));
+            dim3 grid((unsigned)((n + drop_warps - 1) / drop_warps), nb);
+            LAUNCH(KID_RASTER_DROP, s, k_raster_droplets<<<grid, 32 * drop_warps, smem, s>>>(ctx->d_frames, n, mesh, 0u, ctx->dxf, vis, vis_stride));
         }
         uint32_t* rgba = (uint32_t*)(d_rgba + (size_t)f0 * px * 4);
         if (in_is_f64)

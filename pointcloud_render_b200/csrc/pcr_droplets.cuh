@@ -25,7 +25,6 @@ struct TrailPlan { TrailSample s[HISTORY_FRAMES + 1][TRAIL_SAMPLES]; };    // in
 
 struct DropletMeshDev {
     const float* verts;      // [nv][3] object space, as a loader reads the OBJ text
-    const float4* band;      // [n_rings] bounding sphere of the two rings of band i: (0, 0, zc, R)
     const float4* prof;      // [n_rings+1] ring radius, ring z, smooth normal (radial, z)
     float4 bound;            // bounding sphere of the whole mesh (0, 0, zc, R)
     int n_rings, n_segs, nv;
@@ -317,83 +316,78 @@ __device__ __forceinline__ bool triangle_depth(const float* v0, const float* v1,
     return true;
 }
 
-// conservative "does the ray (u,w,1) come within R of c" (R already padded): |c x v|^2 <= R^2 |v|^2
-__device__ __forceinline__ bool ray_near(const float4& c, float u, float w, float vv)
-{
-    const float a = c.y - c.z * w, b = c.z * u - c.x, e = c.x * w - c.y * u;
-    return a * a + b * b + e * e <= c.w * c.w * vv;
-}
-
-// Droplets: one CTA per (frame, point).  The CTA transforms the mesh's vertices to camera space in shared
-// memory (world vertex = M v, then the sphere-centre camera transform — VA-3), then its threads walk the
-// pixels of the instance's screen box: whole-mesh bounding sphere, then per ring band a bounding sphere, then
-// the band's 2*n_segs triangles.  One atomicMin per covered pixel.
+// Droplets: one WARP per (frame, point), triangle-order raster.  The warp transforms the mesh's vertices to
+// camera space in its slice of shared memory (world vertex = M v, then the sphere-centre camera transform —
+// VA-3); then each lane takes triangles, projects the three vertices to get the triangle's (padded) pixel box —
+// one to a few pixels for a 2.5 mm triangle — and runs the VA-3 test on those pixel centres only, merging hits
+// with atomicMin.  Same (pixel, triangle) arithmetic as testing every pixel against every triangle; the min is
+// order independent.  A triangle with a vertex at or behind the eye plane takes the instance's whole screen box.
 __global__ void __launch_bounds__(256)
 k_raster_droplets(const FrameDev* __restrict__ frames, long long n, DropletMeshDev mesh, uint32_t id_base, const float* __restrict__ xf,
                   unsigned long long* __restrict__ vis, long long vis_stride)
 {
-    extern __shared__ __align__(16) float s_cam[];                 // [nv][3] camera-space vertices, then [n_rings] float4 band spheres
-    __shared__ int s_box[4];
-    __shared__ float4 s_bound;
+    extern __shared__ __align__(16) float s_cam[];   // [warps][nv][3] camera-space vertices
     const int b = blockIdx.y;
-    const long long i = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const long long i = (long long)blockIdx.x * warps + warp;
+    if (i >= n) return;
     const FrameDev& f = frames[b];
     const float* M = xf + ((size_t)b * n + i) * 12;
     float m[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) m[k] = __ldg(M + k);
-    float4* s_band = reinterpret_cast<float4*>(s_cam + ((mesh.nv * 3 + 3) & ~3));
-    for (int v = threadIdx.x; v < mesh.nv; v += blockDim.x) {
+    // instance bounding sphere -> screen box (also the early out for droplets off screen / behind the eye)
+    int bx0 = 0, bx1 = -1, by0 = 0, by1 = -1;
+    {
+        const float4 o = mesh.bound;
+        const float X[3] = {m[2] * o.z + m[3], m[6] * o.z + m[7], m[10] * o.z + m[11]};
+        float c[3];
+        to_camera(f, X, c);
+        const float R = o.w * 1.01f + 1e-5f + 4e-6f * (fabsf(c[0]) + fabsf(c[1]) + fabsf(c[2]));
+        if (!(isfinite(m[0] + m[1] + m[2] + m[4] + m[5] + m[6] + m[8] + m[9] + m[10]) && sphere_bbox(f, c[0], c[1], c[2], R, bx0, bx1, by0, by1)))
+            return;                                  // warp-uniform
+    }
+    float* cam = s_cam + (size_t)warp * mesh.nv * 3;
+    for (int v = lane; v < mesh.nv; v += 32) {
         const float ox = __ldg(mesh.verts + 3 * v), oy = __ldg(mesh.verts + 3 * v + 1), oz = __ldg(mesh.verts + 3 * v + 2);
         float X[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) X[r] = fmaf(m[4 * r], ox, fmaf(m[4 * r + 1], oy, fmaf(m[4 * r + 2], oz, m[4 * r + 3])));
-        to_camera(f, X, s_cam + 3 * v);
+        to_camera(f, X, cam + 3 * v);
     }
-    // bounding spheres: object-space centre on the axis -> camera space; radius padded for the f32 transform
-    for (int k = threadIdx.x; k <= mesh.n_rings; k += blockDim.x) {
-        const float4 o = k < mesh.n_rings ? __ldg(mesh.band + k) : mesh.bound;
-        const float X[3] = {m[2] * o.z + m[3], m[6] * o.z + m[7], m[10] * o.z + m[11]};
-        float c[3];
-        to_camera(f, X, c);
-        const float4 sp = make_float4(c[0], c[1], c[2], o.w * 1.01f + 1e-5f + 4e-6f * (fabsf(c[0]) + fabsf(c[1]) + fabsf(c[2])));
-        if (k < mesh.n_rings) s_band[k] = sp;
-        else {
-            s_bound = sp;
-            int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
-            const bool vis_ok = isfinite(m[0] + m[1] + m[2] + m[4] + m[5] + m[6] + m[8] + m[9] + m[10]) &&
-                                sphere_bbox(f, c[0], c[1], c[2], sp.w, x0, x1, y0, y1);
-            s_box[0] = vis_ok ? x0 : 0; s_box[1] = vis_ok ? x1 : -1; s_box[2] = vis_ok ? y0 : 0; s_box[3] = vis_ok ? y1 : -1;
-        }
-    }
-    __syncthreads();
-    const int x0 = s_box[0], x1 = s_box[1], y0 = s_box[2], y1 = s_box[3];
-    if (x1 < x0 || y1 < y0) return;
-    const int bw = x1 - x0 + 1;
-    const long long npx = (long long)bw * (y1 - y0 + 1);
-    const float4 bound = s_bound;
+    __syncwarp();
     unsigned long long* out = vis + (size_t)b * vis_stride;
-    const int ns = mesh.n_segs;
-    for (long long k = threadIdx.x; k < npx; k += blockDim.x) {
-        const int px = x0 + (int)(k % bw), py = y0 + (int)(k / bw);
-        const float u = pix_u(f, px), w = pix_w(f, py);
-        const float vv = fmaf(u, u, fmaf(w, w, 1.0f));
-        if (!ray_near(bound, u, w, vv)) continue;
-        float best = INFINITY;
-        for (int r = 0; r < mesh.n_rings; ++r) {
-            if (!ray_near(s_band[r], u, w, vv)) continue;
-            const float* ring0 = s_cam + 3 * r * ns;
-            const float* ring1 = ring0 + 3 * ns;
-            for (int j = 0; j < ns; ++j) {
-                const int jn = j + 1 == ns ? 0 : j + 1;
-                const float *v0 = ring0 + 3 * j, *v1 = ring0 + 3 * jn, *v2 = ring1 + 3 * j, *v3 = ring1 + 3 * jn;
-                float t;
-                if (triangle_depth(v0, v2, v1, u, w, f.near_clip, f.far_clip, t)) best = fminf(best, t);
-                if (triangle_depth(v1, v2, v3, u, w, f.near_clip, f.far_clip, t)) best = fminf(best, t);
+    const unsigned long long id = (unsigned long long)(id_base + (uint32_t)i);
+    const int ns = mesh.n_segs, ntri = 2 * mesh.n_rings * ns;
+    for (int t = lane; t < ntri; t += 32) {
+        const int quad = t >> 1, r = quad / ns, j = quad - r * ns, jn = j + 1 == ns ? 0 : j + 1;
+        const float* ring0 = cam + 3 * r * ns;
+        const float* ring1 = ring0 + 3 * ns;
+        // the reference's faces per quad: (v0, v2, v1) and (v1, v2, v3)
+        const float* v0 = (t & 1) ? ring0 + 3 * jn : ring0 + 3 * j;
+        const float* v1 = ring1 + 3 * j;
+        const float* v2 = (t & 1) ? ring1 + 3 * jn : ring0 + 3 * jn;
+        int x0 = bx0, x1 = bx1, y0 = by0, y1 = by1;
+        if (v0[2] > 1e-3f && v1[2] > 1e-3f && v2[2] > 1e-3f) {
+            float i0, j0, i1, j1, i2, j2;
+            pixel_of(f, v0[0], v0[1], v0[2], i0, j0);
+            pixel_of(f, v1[0], v1[1], v1[2], i1, j1);
+            pixel_of(f, v2[0], v2[1], v2[2], i2, j2);
+            // A pixel centre can pass VA-3 only inside the projected triangle, up to the float error of the
+            // barycentrics — which, in pixels, grows as the triangle turns edge-on (error ~1e-4 of an edge length
+            // divided by the cosine of the tilt).  Half a pixel of padding covers tilts down to cos ~ 2e-4.
+            constexpr float PAD = 0.5f;
+            x0 = max(x0, (int)ceilf(fminf(i0, fminf(i1, i2)) - PAD)); x1 = min(x1, (int)floorf(fmaxf(i0, fmaxf(i1, i2)) + PAD));
+            y0 = max(y0, (int)ceilf(fminf(j0, fminf(j1, j2)) - PAD)); y1 = min(y1, (int)floorf(fmaxf(j0, fmaxf(j1, j2)) + PAD));
+        }
+        for (int py = y0; py <= y1; ++py) {
+            const float w = pix_w(f, py);
+            for (int px = x0; px <= x1; ++px) {
+                float d;
+                if (triangle_depth(v0, v1, v2, pix_u(f, px), w, f.near_clip, f.far_clip, d))
+                    atomicMin(out + (size_t)py * f.W + px, ((unsigned long long)__float_as_uint(d) << 32) | id);
             }
         }
-        if (best < INFINITY)
-            atomicMin(out + (size_t)py * f.W + px, ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)(id_base + (uint32_t)i));
     }
 }
 

@@ -14,6 +14,9 @@ CONFIGS = {
     "C3": dict(frames=500, points=16384, cols=6, width=1024, height=1024, preset="traj_b0", color_mode=0, radii=True),
     "C4": dict(frames=1000, points=100000, cols=6, width=1920, height=1080, preset="traj_vel", color_mode=2, radii=False),
     "C5": dict(frames=1, points=50_000_000, cols=3, width=4096, height=4096, preset="example", color_mode=0, radii=False),
+    # the droplet scenes of the same two scripts: what traj_renderer.py / traj_vel_renderer.py really draw
+    "C2D": dict(frames=100, points=2048, cols=6, width=1024, height=1024, preset="traj", color_mode=0, radii=False, droplet_trails=2),
+    "C4D": dict(frames=1000, points=100000, cols=6, width=1920, height=1080, preset="traj_vel", color_mode=0, radii=False, droplet_trails=1),
     "H": dict(frames=100, points=1_000_000, cols=3, width=1024, height=1024, preset="traj_ball", color_mode=0, radii=False),
 }
 
