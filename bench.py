@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--frames-per-step", type=int, default=0, help="frames per step per GPU (0 = workload default)")
     ap.add_argument("--ring", type=int, default=0, help="resident frames per GPU (0 = enough to exceed L2)")
     ap.add_argument("--trails", action="store_true", help="also draw the reference's velocity trails (6-column workloads C3/C4)")
+    ap.add_argument("--merge", default="fused", choices=["fused", "nccl"],
+                    help="C5 on several GPUs: z-merge fused into the raster over peer memory (default) or NCCL min all-reduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with events in the timed region")
@@ -290,8 +292,12 @@ def run_point_sharded(args, spec, rank, world, local_rank):
 
     bufs = sharding.point_sharded_buffers(b - a, cam, local.device)          # allocated once, reused every frame
     frames1 = local.unsqueeze(0)
+    fused = world > 1 and args.merge == "fused"
+    mesh = sharding.PeerMesh(ctx, cam) if fused else None
 
     def step():
+        if fused:
+            return sharding.render_point_sharded_fused(ctx, mesh, local, a, n, cam, style, buffers=bufs)
         if world > 1:
             return sharding.render_point_sharded(ctx, local, a, n, cam, style, buffers=bufs)
         # one GPU: the whole-path entry (K1 fused into K2a / K4, nothing materialised)
@@ -346,8 +352,12 @@ def run_point_sharded(args, spec, rank, world, local_rank):
                 "config": {"workload": f"C5: one {n}-point Gaussian cloud at {W}x{H}, preset {spec['preset']}, point-sharded over {world} GPU(s)",
                            "points": n, "width": W, "height": H, "points_per_gpu": b - a,
                            "l2_policy": f"inputs larger than L2 ({(b - a) * 12 / 1e6:.0f} MB of points + {W * H * 8 / 1e6:.0f} MB z-buffer per GPU)",
-                           "parallelism": "single GPU" if world == 1 else f"points sharded over {world} GPUs; C0 all-gather (72 B/rank) + C1 "
-                                          f"ncclAllReduce(int64,min) of {W * H * 8 / 1e6:.0f} MB + byte-MAX all-reduce of {W * H * 4 / 1e6:.0f} MB RGBA8"},
+                           "parallelism": "single GPU" if world == 1 else (
+                               f"points sharded over {world} GPUs; z-merge fused into the raster: winners pushed into the row owner's z-buffer with "
+                               "64-bit atomicMin over NVLink (CUDA IPC peer memory), image pixels stored straight into rank 0's buffer; "
+                               "collectives left: 72 B/rank stats all-gather + two 1-element all-reduces as barriers" if fused else
+                               f"points sharded over {world} GPUs; C0 all-gather (72 B/rank) + C1 "
+                               f"ncclAllReduce(int64,min) of {W * H * 8 / 1e6:.0f} MB + byte-MAX all-reduce of {W * H * 4 / 1e6:.0f} MB RGBA8")},
                 "e2e": None, "gpu_launches": int(counters["launches"] - launches0), "kernels": kernels,
                 "kernel_ms_per_step": kernel_ms / args.steps, "collective_and_gap_ms_per_step": ms / args.steps - kernel_ms / args.steps,
                 "roofline": {"bound": "hbm", "kernel": top[0], "achieved": per_gpu_bytes / (top[1][0] / top[1][1] * 1e-3) / 1e9, "peak": peak,
@@ -356,8 +366,11 @@ def run_point_sharded(args, spec, rank, world, local_rank):
                              "note": "per-GPU algorithmic bytes = shard points*12 + W*H*8 (own z-buffer) + W*H*4/world (image slice)"},
                 "clocks": sampler.summary() if sampler else None, "pairs_last_frame": counters["pairs_last_frame"],
                 "overflow_frames": counters["overflow_frames"],
-                "sphere_pixels": int((_native.keys_to_ids(vis) < n).sum())}
+                "sphere_pixels": int((_native.keys_to_ids(ctx.peer_buffers()[0] if fused else vis) < n).sum()) if not fused else None,
+                "merge": ("fused-peer-memory" if fused else "nccl-allreduce") if world > 1 else None}
         print(json.dumps(line), flush=True)
+    if mesh:
+        mesh.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -294,6 +294,38 @@ int pcr_render_droplet_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int
                               const float* d_rot, const pcr_camera* cams, const pcr_style* style, uint64_t* d_vis,
                               uint8_t* d_rgba, void* stream);
 
+/* ---- fused z-merge over peer memory (point-sharded clouds; no reference counterpart) ----------
+ * Alternative to pcr_render_shard -> ncclAllReduce(min) -> pcr_shade_shard -> byte-MAX all-reduce: every rank owns a
+ * band of image rows of the merged z-buffer; the raster pushes its winners straight into the owner's rows with
+ * 64-bit atomicMin over NVLink WHILE it rasterises the remaining tiles, and the shade kernel reads the merged key
+ * back from the owner and stores each pixel it won directly into rank dst_rank's image.  The only collectives
+ * left are three tiny ones used as barriers (the 72-byte stats all-gather and two 1-element all-reduces).
+ *
+ * Per frame, on every rank, stream-ordered:
+ *   pcr_peer_begin_frame                      floor keys into the rows this rank owns
+ *   pcr_stats_partial -> all-gather -> pcr_finalize_stats      (the all-gather also orders every rank's
+ *                                                               begin_frame before anybody's pushes)
+ *   pcr_render_shard_peer                     K2/K3 into the local d_vis + pushes into the owners' rows
+ *   barrier  (any collective)                 all pushes have landed
+ *   pcr_shade_shard_peer                      K4: pixels this rank won / owns -> image of dst_rank
+ *   barrier                                   the image on dst_rank is complete; merged rows may be reused
+ * Set-up, once: pcr_peer_alloc on every rank, exchange the buffers' IPC handles (pcr_ipc_export / pcr_ipc_open;
+ * ranks inside ONE process pass raw pointers), pcr_peer_set.  At most 8 ranks. */
+int pcr_peer_alloc(pcr_ctx* ctx, int width, int height, void** d_merged, void** d_image);
+int pcr_ipc_export(pcr_ctx* ctx, const void* d_ptr, uint8_t handle[64]);      /* cudaIpcGetMemHandle */
+int pcr_ipc_open(pcr_ctx* ctx, const uint8_t handle[64], void** d_ptr);       /* cudaIpcOpenMemHandle */
+int pcr_ipc_close(pcr_ctx* ctx, void* d_ptr);
+/* merged_ptrs / image_ptrs: HOST arrays of `world` device pointers in rank order; entry [rank] must be this
+ * context's own buffers.  world == 0 detaches. */
+int pcr_peer_set(pcr_ctx* ctx, int rank, int world, int dst_rank, void* const* merged_ptrs, void* const* image_ptrs);
+int pcr_peer_begin_frame(pcr_ctx* ctx, const pcr_camera* cam, const pcr_style* style, void* stream);
+int pcr_render_shard_peer(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols, const float* d_radius,
+                          const float* d_rgb, const double* d_stats10, uint32_t id_base, const pcr_camera* cam,
+                          const pcr_style* style, uint64_t* d_vis, void* stream);
+int pcr_shade_shard_peer(pcr_ctx* ctx, const uint64_t* d_vis, const void* d_in, int in_is_f64, int64_t n, int cols,
+                         const float* d_radius, const float* d_rgb, const double* d_stats10, uint32_t id_base,
+                         const pcr_camera* cam, const pcr_style* style, void* stream);
+
 /* Counters of the last pcr_render / pcr_render_frames call (synchronises `stream`):
  * out[0] = kernels launched, out[1] = (tile,sphere) pairs of the last frame,
  * out[2] = frames that overflowed pair_capacity, out[3] = spheres culled (last frame). */

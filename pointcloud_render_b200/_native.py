@@ -26,6 +26,8 @@ SYMBOLS = (
     "pcr_zmin", "pcr_zmerge_nccl", "pcr_stats_partial", "pcr_standardize_with_stats", "pcr_counters",
     "pcr_transform_coordinates", "pcr_profile", "pcr_profile_read", "pcr_kernel_name", "pcr_set_occlusion", "pcr_finalize_stats", "pcr_velocity_trails", "pcr_render_shard", "pcr_shade_shard",
     "pcr_set_droplet_mesh", "pcr_droplet_transforms", "pcr_history_trails", "pcr_render_droplet_frames",
+    "pcr_peer_alloc", "pcr_ipc_export", "pcr_ipc_open", "pcr_ipc_close", "pcr_peer_set", "pcr_peer_begin_frame",
+    "pcr_render_shard_peer", "pcr_shade_shard_peer",
 )
 HISTORY_FRAMES, MAX_CTRL = 20, 21                   # PCR_HISTORY_FRAMES, PCR_MAX_CTRL
 TRAILS_NONE, TRAILS_VELOCITY, TRAILS_HISTORY = 0, 1, 2
@@ -99,6 +101,14 @@ def load_library():
     L.pcr_droplet_transforms.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     L.pcr_history_trails.argtypes = [vp, vp, i32, vp, i64, vp, vp, vp]
     L.pcr_render_droplet_frames.argtypes = [vp, vp, i32, i64, i32, i32, i32, vp, camp, styp, vp, vp, vp]
+    L.pcr_peer_alloc.argtypes = [vp, i32, i32, ctypes.POINTER(vp), ctypes.POINTER(vp)]
+    L.pcr_ipc_export.argtypes = [vp, vp, vp]
+    L.pcr_ipc_open.argtypes = [vp, vp, ctypes.POINTER(vp)]
+    L.pcr_ipc_close.argtypes = [vp, vp]
+    L.pcr_peer_set.argtypes = [vp, i32, i32, i32, ctypes.POINTER(vp), ctypes.POINTER(vp)]
+    L.pcr_peer_begin_frame.argtypes = [vp, camp, styp, vp]
+    L.pcr_render_shard_peer.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp, u32, camp, styp, vp, vp]
+    L.pcr_shade_shard_peer.argtypes = [vp, vp, vp, i32, i64, i32, vp, vp, vp, u32, camp, styp, vp]
     L.pcr_profile.argtypes = [vp, i32]
     L.pcr_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), i32]
     L.pcr_kernel_name.argtypes = [i32]
@@ -389,6 +399,58 @@ class Context:
                                                            _stream_ptr(stream)))
         return (rgba, vis) if (want_vis or out_vis is not None) else rgba
 
+    # ---- fused z-merge over peer memory (point-sharded clouds) -----------------------------
+    def peer_alloc(self, width, height):
+        """This rank's merged z-buffer and image (library-owned cudaMalloc blocks): raw device pointers."""
+        m, im = ctypes.c_void_p(), ctypes.c_void_p()
+        self._check(self.lib.pcr_peer_alloc(self.handle, int(width), int(height), ctypes.byref(m), ctypes.byref(im)))
+        self.peer_shape = (int(height), int(width))
+        return m.value, im.value
+
+    def ipc_export(self, ptr):
+        h = (ctypes.c_uint8 * 64)()
+        self._check(self.lib.pcr_ipc_export(self.handle, ctypes.c_void_p(ptr), h))
+        return bytes(h)
+
+    def ipc_open(self, handle):
+        out = ctypes.c_void_p()
+        buf = (ctypes.c_uint8 * 64).from_buffer_copy(handle)
+        self._check(self.lib.pcr_ipc_open(self.handle, buf, ctypes.byref(out)))
+        return out.value
+
+    def ipc_close(self, ptr):
+        self._check(self.lib.pcr_ipc_close(self.handle, ctypes.c_void_p(ptr)))
+
+    def peer_set(self, rank, world, merged_ptrs, image_ptrs, dst_rank=0):
+        arr_m = (ctypes.c_void_p * max(world, 1))(*[ctypes.c_void_p(p) for p in merged_ptrs])
+        arr_i = (ctypes.c_void_p * max(world, 1))(*[ctypes.c_void_p(p) for p in image_ptrs])
+        self._check(self.lib.pcr_peer_set(self.handle, int(rank), int(world), int(dst_rank), arr_m, arr_i))
+
+    def peer_begin_frame(self, cam, style, stream=None):
+        self._check(self.lib.pcr_peer_begin_frame(self.handle, ctypes.byref(cam), ctypes.byref(style), _stream_ptr(stream)))
+
+    def render_shard_peer(self, pts, stats10, cam, style, id_base=0, radius=None, rgb=None, out_vis=None, stream=None):
+        import torch
+        n, cols = pts.shape
+        vis = out_vis if out_vis is not None else torch.empty((cam.height, cam.width), dtype=torch.int64, device=pts.device)
+        self._check(self.lib.pcr_render_shard_peer(self.handle, _ptr(pts) if n else None, int(pts.dtype == torch.float64), n, cols,
+                                                   _ptr(radius), _ptr(rgb), _ptr(stats10), int(id_base), ctypes.byref(cam),
+                                                   ctypes.byref(style), _ptr(vis), _stream_ptr(stream)))
+        return vis
+
+    def shade_shard_peer(self, vis, pts, stats10, cam, style, id_base=0, radius=None, rgb=None, stream=None):
+        import torch
+        n, cols = pts.shape
+        self._check(self.lib.pcr_shade_shard_peer(self.handle, _ptr(vis), _ptr(pts) if n else None, int(pts.dtype == torch.float64), n, cols,
+                                                  _ptr(radius), _ptr(rgb), _ptr(stats10), int(id_base), ctypes.byref(cam),
+                                                  ctypes.byref(style), _stream_ptr(stream)))
+
+    def peer_buffers(self):
+        """torch views (no copy) of this rank's merged keys (H,W) int64 and image (H,W,4) uint8."""
+        H, W = self.peer_shape
+        m, im = self.peer_alloc(W, H)
+        return _device_view(m, (H, W), "int64", self.device), _device_view(im, (H, W, 4), "uint8", self.device)
+
     # ---- merge ---------------------------------------------------------------------------
     def zmin_(self, dst, src, stream=None):
         self._check(self.lib.pcr_zmin(self.handle, _ptr(dst), _ptr(src), dst.numel(), _stream_ptr(stream)))
@@ -414,6 +476,16 @@ class Context:
         out = (ctypes.c_int64 * 4)()
         self._check(self.lib.pcr_counters(self.handle, out, _stream_ptr(stream)))
         return {"launches": out[0], "pairs_last_frame": out[1], "overflow_frames": out[2]}
+
+
+def _device_view(ptr, shape, dtype, device):
+    """A torch tensor aliasing raw device memory (library-owned; the caller keeps the context alive)."""
+    import torch
+
+    class _Mem:
+        __cuda_array_interface__ = {"shape": tuple(shape), "typestr": {"int64": "<i8", "uint8": "|u1"}[dtype], "data": (int(ptr), False),
+                                    "version": 3, "strides": None}
+    return torch.as_tensor(_Mem(), device=f"cuda:{device}")
 
 
 def keys_to_ids(vis):

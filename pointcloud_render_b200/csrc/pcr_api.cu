@@ -26,11 +26,12 @@ constexpr int MAX_STAT_BLOCKS = 1184;   // 148 SMs x 8
 
 enum KernelId { KID_STATS = 0, KID_TRANSFORM, KID_PROJECT, KID_SCAN, KID_SCATTER, KID_RASTER, KID_HIZ, KID_SHADE,
                 KID_ZMIN, KID_AXIS, KID_FILL, KID_MEAN, KID_LUT, KID_DROP_PREP, KID_FILL_FLOOR, KID_RASTER_POLY, KID_RASTER_DROP,
-                KID_SHADE_DROP, KID_COUNT };
+                KID_SHADE_DROP, KID_PEER_INIT, KID_SHADE_PEER, KID_COUNT };
 const char* const kKernelNames[KID_COUNT] = {"k_stats", "k_transform", "k_project_count", "k_scan_tiles", "k_scatter",
                                              "k_raster_tiles", "k_hiz", "k_shade", "k_zmin", "k_axis_transform",
                                              "k_fill_tiles", "k_mean_sequential", "k_build_floor_lut", "k_droplet_prepare",
-                                             "k_fill_floor", "k_raster_polylines", "k_raster_droplets", "k_shade_droplets"};
+                                             "k_fill_floor", "k_raster_polylines", "k_raster_droplets", "k_shade_droplets", "k_peer_init_rows",
+                                             "k_shade_peer"};
 constexpr size_t PROF_MAX_RECORDS = 1 << 16;
 
 struct ProfRec { int kid; cudaEvent_t a, b; };
@@ -86,6 +87,13 @@ struct pcr_ctx {
     float *stage_radius = nullptr, *stage_rgb = nullptr;
 
     long long last_overflow_frames = 0;
+
+    // fused z-merge over peer memory (pcr_peer_*): this rank's merged z-buffer / image (cudaMalloc, so that
+    // cudaIpcGetMemHandle maps them at offset 0) and the pointer table of every rank's
+    void* peer_merged = nullptr;
+    void* peer_image = nullptr;
+    int peer_w = 0, peer_h = 0;
+    PeerDev peer = {};
 
     // droplet scene (pcr_render_droplet_frames): mesh tables, spline plan, per-frame stats of the whole
     // buffer, per-point matrices / control points of one batch — all lazily allocated
@@ -345,9 +353,11 @@ int launch_shade(pcr_ctx* ctx, const StyleDev& st, const uint64_t* vis, long lon
 
 int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long in_stride, const RawSrc* raw, long long n, int nb,
                   uint32_t id_base, const StyleDev& st, int W, int H, uint64_t* vis, long long vis_stride,
-                  uint8_t* rgba, long long rgba_stride, int owner_only, cudaStream_t stream)
+                  uint8_t* rgba, long long rgba_stride, int owner_only, cudaStream_t stream, const PeerDev* push = nullptr)
 {
     BinDev bin = bin_of(ctx);
+    PeerDev no_peer = {};                              // world == 0: nothing is pushed
+    const PeerDev peer_final = push ? *push : no_peer;
     const int tiles = ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
     // K2 blocks own contiguous point chunks and histogram their pairs in shared memory when the
     // tile count allows it (count: 4 B/tile, scatter: 8 B/tile)
@@ -362,7 +372,7 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
     const long long slots = 2 * ctx->max_points;       // survivor slots per frame: sphere + trail per point
 
     // one binning + raster pass over `np` spheres (sphere i = point i*step)
-    auto pass = [&](long long np, int step, const unsigned int* hz, int seeded, int do_trails) -> int {
+    auto pass = [&](long long np, int step, const unsigned int* hz, int seeded, int do_trails, const PeerDev& peer) -> int {
         unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((np + 2047) / 2048, std::max(1, 2 * resident / nb)));
         if (!use_smem) gx = (unsigned)std::max<long long>(1, (np + BIN_THREADS * 4 - 1) / (BIN_THREADS * 4));
         gx = std::min<unsigned>(gx, (unsigned)ctx->gx_cap);
@@ -395,10 +405,10 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
             dim3 grid((unsigned)std::max(1, std::min(raster_ctas, tiles * nb)));
             if (do_trails)
                 LAUNCH(KID_RASTER, stream, k_raster_tiles<true><<<grid, RASTER_THREADS, 0, stream>>>(
-                    ctx->d_frames, st, ctx->sph, ctx->rect, ctx->ext, slots, bin, id_base, (uint32_t)step, cap_id_base, v, vis_stride, nb, np, seeded, (int)gx));
+                    ctx->d_frames, st, ctx->sph, ctx->rect, ctx->ext, slots, bin, id_base, (uint32_t)step, cap_id_base, v, vis_stride, nb, np, seeded, (int)gx, peer));
             else
                 LAUNCH(KID_RASTER, stream, k_raster_tiles<false><<<grid, RASTER_THREADS, 0, stream>>>(
-                    ctx->d_frames, st, ctx->sph, ctx->rect, ctx->ext, slots, bin, id_base, (uint32_t)step, 0u, v, vis_stride, nb, np, seeded, (int)gx));
+                    ctx->d_frames, st, ctx->sph, ctx->rect, ctx->ext, slots, bin, id_base, (uint32_t)step, 0u, v, vis_stride, nb, np, seeded, (int)gx, peer));
         }
         return PCR_OK;
     };
@@ -407,7 +417,7 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
     if (occl && n > ctx->occlusion_step) {
         // occluder pre-pass (every step-th point, true ids) -> Hi-Z -> main pass seeded with its keys
         const int step = ctx->occlusion_step;
-        int rc = pass((n + step - 1) / step, step, nullptr, 0, 0);       // trails are never occluders
+        int rc = pass((n + step - 1) / step, step, nullptr, 0, 0, no_peer);       // trails are never occluders; only the final pass pushes
         if (rc) return rc;
         const int hzn = ((W + HZ_W - 1) / HZ_W) * ((H + HZ_H - 1) / HZ_H);
         dim3 grid((unsigned)((hzn + 255) / 256), nb);
@@ -415,10 +425,10 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         const int hzn2 = (((W + HZ_W - 1) / HZ_W + 3) / 4) * (((H + HZ_H - 1) / HZ_H + 3) / 4);
         dim3 grid2((unsigned)((hzn2 + 255) / 256), nb);
         LAUNCH(KID_HIZ, stream, k_hiz2<<<grid2, 256, 0, stream>>>(ctx->d_frames, ctx->hz, ctx->hz_cap));
-        rc = pass(n, 1, ctx->hz, 1, trails);
+        rc = pass(n, 1, ctx->hz, 1, trails, peer_final);
         if (rc) return rc;
     } else {
-        int rc = pass(n, 1, nullptr, 0, trails);
+        int rc = pass(n, 1, nullptr, 0, trails, peer_final);
         if (rc) return rc;
     }
     if (rgba) return launch_shade(ctx, st, vis, vis_stride, pos, attr, in_stride, raw, n, nb, id_base, owner_only, W, H, rgba, rgba_stride, stream);
@@ -547,7 +557,7 @@ void pcr_destroy(pcr_ctx* ctx)
     void* frees[] = {ctx->surv_count, ctx->ext, ctx->sph, ctx->rect, ctx->partials, ctx->stats, ctx->done, ctx->counts, ctx->offsets,
                      ctx->cursor, ctx->pairs, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
                      ctx->stage_rgba[0], ctx->stage_rgba[1], ctx->stage_vis[0], ctx->stage_vis[1], ctx->stage_radius, ctx->stage_rgb,
-                     ctx->mesh_verts, ctx->mesh_prof, ctx->plan, ctx->dstats, ctx->dxf, ctx->dctrl, ctx->dcount};
+                     ctx->peer_merged, ctx->peer_image, ctx->mesh_verts, ctx->mesh_prof, ctx->plan, ctx->dstats, ctx->dxf, ctx->dctrl, ctx->dcount};
     for (void* p : frees) if (p) cudaFree(p);
     if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
     for (int k = 0; k < RING_SLOTS; ++k) if (ctx->ring_ev[k]) cudaEventDestroy(ctx->ring_ev[k]);
@@ -1212,6 +1222,150 @@ int pcr_render_droplet_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int
                                                                                   raw_frames<float>(&raw), g0, n, mesh, ctx->dxf, ctx->dctrl,
                                                                                   ctx->dcount, rgba, px));
     }
+    return leave(ctx, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused z-merge over peer memory (point-sharded clouds)
+// ------------------------------------------------------------------------------------------
+int pcr_peer_alloc(pcr_ctx* ctx, int width, int height, void** d_merged, void** d_image)
+{
+    if (!ctx) return PCR_ERR_INVALID;
+    if (width < 1 || height < 1 || width > ctx->max_w || height > ctx->max_h) return fail(ctx, PCR_ERR_CAPACITY, "pcr_peer_alloc: frame larger than the context");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->peer_w != width || ctx->peer_h != height) {
+        CK(cudaDeviceSynchronize());
+        if (ctx->peer_merged) CK(cudaFree(ctx->peer_merged));
+        if (ctx->peer_image) CK(cudaFree(ctx->peer_image));
+        ctx->peer_merged = ctx->peer_image = nullptr; ctx->peer_w = ctx->peer_h = 0; ctx->peer.world = 0;
+        CK(cudaMalloc(&ctx->peer_merged, sizeof(uint64_t) * (size_t)width * height));
+        CK(cudaMalloc(&ctx->peer_image, sizeof(uint32_t) * (size_t)width * height));
+        ctx->peer_w = width; ctx->peer_h = height;
+    }
+    if (d_merged) *d_merged = ctx->peer_merged;
+    if (d_image) *d_image = ctx->peer_image;
+    return PCR_OK;
+}
+
+int pcr_ipc_export(pcr_ctx* ctx, const void* d_ptr, uint8_t handle[64])
+{
+    if (!ctx) return PCR_ERR_INVALID;
+    if (!d_ptr || !handle) return fail(ctx, PCR_ERR_INVALID, "pcr_ipc_export: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)));
+    memcpy(handle, &h, 64);
+    return PCR_OK;
+}
+
+int pcr_ipc_open(pcr_ctx* ctx, const uint8_t handle[64], void** d_ptr)
+{
+    if (!ctx) return PCR_ERR_INVALID;
+    if (!d_ptr || !handle) return fail(ctx, PCR_ERR_INVALID, "pcr_ipc_open: NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PCR_OK;
+}
+
+int pcr_ipc_close(pcr_ctx* ctx, void* d_ptr)
+{
+    if (!ctx) return PCR_ERR_INVALID;
+    if (!d_ptr) return PCR_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaIpcCloseMemHandle(d_ptr));
+    return PCR_OK;
+}
+
+int pcr_peer_set(pcr_ctx* ctx, int rank, int world, int dst_rank, void* const* merged_ptrs, void* const* image_ptrs)
+{
+    if (!ctx) return PCR_ERR_INVALID;
+    if (world == 0) { ctx->peer.world = 0; return PCR_OK; }
+    if (world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || dst_rank < 0 || dst_rank >= world || !merged_ptrs || !image_ptrs)
+        return fail(ctx, PCR_ERR_INVALID, "pcr_peer_set: bad rank / world (at most 8 ranks)");
+    if (!ctx->peer_merged) return fail(ctx, PCR_ERR_INVALID, "pcr_peer_set: call pcr_peer_alloc first");
+    PeerDev p = {};
+    for (int r = 0; r < world; ++r) {
+        if (!merged_ptrs[r] || !image_ptrs[r]) return fail(ctx, PCR_ERR_INVALID, "pcr_peer_set: NULL peer pointer");
+        p.merged[r] = (unsigned long long*)merged_ptrs[r];
+        p.image[r] = (uint32_t*)image_ptrs[r];
+    }
+    if (p.merged[rank] != ctx->peer_merged || p.image[rank] != ctx->peer_image)
+        return fail(ctx, PCR_ERR_INVALID, "pcr_peer_set: entry [rank] must be this context's own buffers");
+    p.world = world; p.rank = rank; p.dst = dst_rank;
+    p.base = ctx->peer_h / world; p.rem = ctx->peer_h % world;
+    ctx->peer = p;
+    return PCR_OK;
+}
+
+int pcr_peer_begin_frame(pcr_ctx* ctx, const pcr_camera* cam, const pcr_style* style, void* stream)
+{
+    if (!ctx) return PCR_ERR_INVALID;
+    if (!cam || !style) return fail(ctx, PCR_ERR_INVALID, "pcr_peer_begin_frame: NULL argument");
+    if (ctx->peer.world < 1) return fail(ctx, PCR_ERR_INVALID, "pcr_peer_begin_frame: call pcr_peer_set first");
+    if (cam->width != ctx->peer_w || cam->height != ctx->peer_h) return fail(ctx, PCR_ERR_INVALID, "camera does not match pcr_peer_alloc");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = enter(ctx, s);
+    if (rc) return rc;
+    if ((rc = upload_frames(ctx, cam, 1, s))) return rc;
+    const PeerDev& p = ctx->peer;
+    const int y0 = p.rank * p.base + std::min(p.rank, p.rem), y1 = y0 + p.base + (p.rank < p.rem ? 1 : 0);
+    if (y1 > y0) {
+        dim3 grid((unsigned)((cam->width + 63) / 64), (unsigned)((y1 - y0 + 3) / 4));
+        LAUNCH(KID_PEER_INIT, s, k_peer_init_rows<<<grid, 256, 0, s>>>(ctx->d_frames, to_style_dev(style), p, y0, y1));
+    }
+    return leave(ctx, s);
+}
+
+int pcr_render_shard_peer(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols, const float* d_radius, const float* d_rgb,
+                          const double* d_stats10, uint32_t id_base, const pcr_camera* cam, const pcr_style* style, uint64_t* d_vis,
+                          void* stream)
+{
+    int rc = check_common(ctx, n, cols, style);
+    if (rc) return rc;
+    if (!cam || !d_vis || !d_stats10 || (n > 0 && !d_in)) return fail(ctx, PCR_ERR_INVALID, "pcr_render_shard_peer: NULL buffer");
+    if (ctx->peer.world < 1) return fail(ctx, PCR_ERR_INVALID, "pcr_render_shard_peer: call pcr_peer_set first");
+    if (cam->width != ctx->peer_w || cam->height != ctx->peer_h) return fail(ctx, PCR_ERR_INVALID, "camera does not match pcr_peer_alloc");
+    if ((unsigned long long)id_base + (unsigned long long)n > 0xFFFFFFFEull) return fail(ctx, PCR_ERR_INVALID, "point id overflow");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = enter(ctx, s))) return rc;
+    if ((rc = upload_frames(ctx, cam, 1, s))) return rc;
+    StyleDev st = to_style_dev(style);
+    st.trails = 0;
+    const RawSrc raw = {d_in, in_is_f64, n * cols, cols, d_stats10, d_radius, d_rgb};
+    const long long px = (long long)cam->width * cam->height;
+    rc = launch_render(ctx, nullptr, nullptr, 0, &raw, n, 1, id_base, st, cam->width, cam->height, d_vis, px, nullptr, px, 0, s, &ctx->peer);
+    if (rc) return rc;
+    return leave(ctx, s);
+}
+
+int pcr_shade_shard_peer(pcr_ctx* ctx, const uint64_t* d_vis, const void* d_in, int in_is_f64, int64_t n, int cols, const float* d_radius,
+                         const float* d_rgb, const double* d_stats10, uint32_t id_base, const pcr_camera* cam, const pcr_style* style,
+                         void* stream)
+{
+    int rc = check_common(ctx, n, cols, style);
+    if (rc) return rc;
+    if (!cam || !d_vis || !d_stats10 || (n > 0 && !d_in)) return fail(ctx, PCR_ERR_INVALID, "pcr_shade_shard_peer: NULL buffer");
+    if (ctx->peer.world < 1) return fail(ctx, PCR_ERR_INVALID, "pcr_shade_shard_peer: call pcr_peer_set first");
+    if (cam->width != ctx->peer_w || cam->height != ctx->peer_h) return fail(ctx, PCR_ERR_INVALID, "camera does not match pcr_peer_alloc");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = enter(ctx, s))) return rc;
+    if ((rc = upload_frames(ctx, cam, 1, s))) return rc;
+    StyleDev st = to_style_dev(style);
+    st.trails = 0;
+    FloorLut lut;
+    if ((rc = floor_lut(ctx, st, s, &lut))) return rc;
+    const RawSrc raw = {d_in, in_is_f64, n * cols, cols, d_stats10, d_radius, d_rgb};
+    dim3 grid((unsigned)((cam->width + 63) / 64), (unsigned)((cam->height + 3) / 4));
+    if (in_is_f64)
+        LAUNCH(KID_SHADE_PEER, s, k_shade_peer<double><<<grid, 256, 0, s>>>(ctx->d_frames, st, lut, d_vis, raw_frames<double>(&raw), n, id_base, ctx->peer));
+    else
+        LAUNCH(KID_SHADE_PEER, s, k_shade_peer<float><<<grid, 256, 0, s>>>(ctx->d_frames, st, lut, d_vis, raw_frames<float>(&raw), n, id_base, ctx->peer));
     return leave(ctx, s);
 }
 

@@ -14,6 +14,11 @@ collective anywhere; both modes are new:
                 ncclAllReduce(ncclInt64, ncclMin) over NVLink, exact and order independent.
             Shading then runs owner-only and the RGBA8 slices are assembled with a byte MAX.
 
+            Fused alternative (render_point_sharded_fused): no big collective at all — every rank owns a band
+            of image rows of the merged z-buffer, the raster pushes its winners into the owner's rows with
+            64-bit atomicMin over NVLink while it is still rasterising, and the shade kernel stores each pixel
+            it won directly into rank 0's image.  Peer memory is mapped with CUDA IPC (PeerMesh).
+
 The collectives run on whatever backend the process group has (nccl on the GPU box, gloo in the
 CPU tests); the compute between them is the pcr C ABI.
 """
@@ -115,3 +120,66 @@ def render_point_sharded(ctx, pts_local, id_base, n_total, cam, style, radius=No
                            out_rgba=b.get("rgba"))
     assemble_image_(rgba, group)
     return vis, rgba
+
+
+class PeerMesh:
+    """Peer-memory set-up of the fused merge: every rank allocates its merged z-buffer + image inside libpcr
+    (cudaMalloc), the 64-byte CUDA IPC handles are all-gathered, every rank maps every other rank's buffers
+    over NVLink and hands the pointer table to its context (pcr_peer_set).  One process per GPU."""
+
+    def __init__(self, ctx, cam, group=None, dst_rank=0):
+        import torch
+        import torch.distributed as dist
+        self.ctx, self.group = ctx, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        dev = torch.device("cuda", ctx.device)
+        m, im = ctx.peer_alloc(cam.width, cam.height)
+        mine = torch.frombuffer(bytearray(ctx.ipc_export(m) + ctx.ipc_export(im)), dtype=torch.uint8).to(dev)
+        allh = torch.empty((self.world, 128), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        allh = allh.cpu().numpy()
+        self.opened, merged, image = [], [], []
+        for r in range(self.world):
+            if r == self.rank:
+                merged.append(m)
+                image.append(im)
+            else:
+                pm, pi = ctx.ipc_open(allh[r, :64].tobytes()), ctx.ipc_open(allh[r, 64:].tobytes())
+                self.opened += [pm, pi]
+                merged.append(pm)
+                image.append(pi)
+        ctx.peer_set(self.rank, self.world, merged, image, dst_rank=dst_rank)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.dst_rank = dst_rank
+
+    def barrier(self):
+        """Stream-ordered cross-rank barrier: a 1-element all-reduce (every rank's earlier kernels — and the
+        remote reductions / stores they issued — complete before any rank's later kernels start)."""
+        import torch.distributed as dist
+        dist.all_reduce(self.flag, group=self.group)
+
+    def close(self):
+        import torch
+        torch.cuda.synchronize()
+        self.barrier()
+        torch.cuda.synchronize()
+        self.ctx.peer_set(0, 0, [], [])
+        for p in self.opened:
+            self.ctx.ipc_close(p)
+        self.opened = []
+
+
+def render_point_sharded_fused(ctx, mesh, pts_local, id_base, n_total, cam, style, radius=None, rgb=None, buffers=None):
+    """The point-sharded path with the z-merge fused into the raster (see PeerMesh): returns (local keys,
+    image) — the image is complete on rank mesh.dst_rank only (a view of its peer image buffer), None elsewhere.
+    Stream-ordered, no host synchronisation; three tiny collectives per frame."""
+    import torch
+    b = buffers or {}
+    ctx.peer_begin_frame(cam, style)
+    part = ctx.stats_partial(pts_local)
+    stats = allgather_stats_device(ctx, part, n_total, pts_local.dtype == torch.float64, mesh.group)   # also: every rank's rows are initialised
+    vis = ctx.render_shard_peer(pts_local, stats, cam, style, id_base=id_base, radius=radius, rgb=rgb, out_vis=b.get("vis"))
+    mesh.barrier()                                                   # all pushes have landed
+    ctx.shade_shard_peer(vis, pts_local, stats, cam, style, id_base=id_base, radius=radius, rgb=rgb)
+    mesh.barrier()                                                   # the image is complete; rows may be reused
+    return vis, (ctx.peer_buffers()[1] if mesh.rank == mesh.dst_rank else None)

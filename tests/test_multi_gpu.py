@@ -25,3 +25,4 @@ def test_frame_and_point_sharding_over_nccl():
     line = [l for l in res.stdout.splitlines() if l.startswith("{")][-1]
     rep = json.loads(line)
     assert rep["frames_identical"] and rep["points_keys_identical"] and rep["points_image_identical"]
+    assert rep["fused_keys_identical"] and rep["fused_image_identical"]

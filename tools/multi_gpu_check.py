@@ -81,12 +81,28 @@ def main():
         report["stats_path_max_abs_diff"] = float((own - pos4).abs().max())
         ids = _native.keys_to_ids(vis)
         report["sphere_pixels"] = int((ids < n).sum())
+    # ---- 3. points, fused merge over peer memory (CUDA IPC + atomicMin over NVLink, no big collective) ----
+    mesh = sharding.PeerMesh(ctx, cam)
+    local = torch.from_numpy(cloud[a:b]).to(dev)
+    for _ in range(2):                                               # twice: the buffers are reused
+        visf, rgbaf = sharding.render_point_sharded_fused(ctx, mesh, local, a, n, cam, style)
+    torch.cuda.synchronize()
+    if rank == 0:
+        report["fused_image_identical"] = bool(torch.equal(rgbaf, rgba))
+    rows = sharding.frame_shard(H, rank, world)
+    mine = ctx.peer_buffers()[0][rows[0]:rows[1]]
+    report_rows = torch.tensor([int(torch.equal(mine, vis[rows[0]:rows[1]]))], device=dev)
+    dist.all_reduce(report_rows, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        report["fused_keys_identical"] = bool(report_rows.item())
+    mesh.close()
     ctx.close()
     dist.barrier()
     if rank == 0:
         print(json.dumps(report), flush=True)
         ok = report["frames_identical"] and report["points_keys_identical"] and report["points_image_identical"] \
-            and report["two_step_keys_identical"] and report["two_step_image_max_abs_diff"] <= 1
+            and report["two_step_keys_identical"] and report["two_step_image_max_abs_diff"] <= 1 \
+            and report["fused_image_identical"] and report["fused_keys_identical"]
         dist.destroy_process_group()
         sys.exit(0 if ok else 1)
     dist.destroy_process_group()
