@@ -56,10 +56,14 @@ struct pcr_ctx {
     int gx_cap = 0;
     double *partials = nullptr, *stats = nullptr;
     unsigned int* done = nullptr;
-    unsigned int *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *pairs = nullptr, *overflow = nullptr;
+    unsigned int *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *overflow = nullptr;
+    float4* p_sph = nullptr;          // per (tile, primitive) pair, in tile order (K2b -> K3): centre + r^2,
+    unsigned int *p_cull = nullptr, *p_id = nullptr;   // cull word, key id,
+    float4* p_ext = nullptr;          // capsule end B — allocated when the first frames with trails arrive
+    int raster_ctas_per_sm[2] = {4, 2};   // k_raster_tiles<false / true>: resident CTAs per SM (occupancy query)
     unsigned long long* stat_pairs = nullptr;
     unsigned int *item_count = nullptr, *item_next = nullptr;
-    uint2* items = nullptr;
+    uint4* items = nullptr;
     int item_cap = 0;
     int smem_optin = 48 * 1024;       // max dynamic shared memory per block (opt-in)
     float* lut = nullptr;             // floor form-factor table (LUT_N^2), rebuilt when the scene constants change
@@ -234,7 +238,8 @@ void to_frame_dev(const pcr_frame& f, FrameDev* d)
 BinDev bin_of(pcr_ctx* c)
 {
     BinDev b;
-    b.counts = c->counts; b.offsets = c->offsets; b.cursor = c->cursor; b.pairs = c->pairs;
+    b.counts = c->counts; b.offsets = c->offsets; b.cursor = c->cursor;
+    b.p_sph = c->p_sph; b.p_cull = c->p_cull; b.p_id = c->p_id; b.p_ext = c->p_ext;
     b.overflow = c->overflow; b.stat_pairs = c->stat_pairs; b.tiles_cap = c->tiles_cap; b.pair_cap = c->pair_cap;
     b.item_count = c->item_count; b.item_next = c->item_next; b.items = c->items; b.item_cap = c->item_cap;
     b.surv_count = c->surv_count; b.gx_cap = c->gx_cap;
@@ -338,7 +343,7 @@ int launch_shade(pcr_ctx* ctx, const StyleDev& st, const uint64_t* vis, long lon
     FloorLut lut;
     int rc = floor_lut(ctx, st, stream, &lut);
     if (rc) return rc;
-    dim3 grid((unsigned)((W + 63) / 64), (unsigned)((H + 3) / 4), nb);
+    dim3 grid((unsigned)((W + 63) / 64), (unsigned)((H + 4 * SHADE_ROWS - 1) / (4 * SHADE_ROWS)), nb);
     if (!raw)
         LAUNCH(KID_SHADE, stream, k_shade<float, false><<<grid, 256, 0, stream>>>(ctx->d_frames, st, lut, vis, vis_stride, pos, attr, in_stride,
                                                                                  raw_frames<float>(nullptr), n, id_base, owner_only, (uint32_t*)rgba, rgba_stride));
@@ -363,12 +368,16 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
     // tile count allows it (count: 4 B/tile, scatter: 8 B/tile)
     const int use_smem = (size_t)tiles * 8 <= (size_t)ctx->smem_optin ? 1 : 0;
     const int resident = ctx->num_sms * (2048 / BIN_THREADS);
-    const int raster_ctas = ctx->num_sms * 4;          // k_raster_tiles: 4 CTAs of 256 threads resident per SM (register bound)
     unsigned long long* v = (unsigned long long*)vis;
     // velocity trails (a second primitive per point) only exist in the fused whole-path entry
     const int trails = raw && st.trails == 1 && raw->cols == 6 ? 1 : 0;
     if (trails && 2 * (unsigned long long)n > 0xFFFFFFF0ull) return fail(ctx, PCR_ERR_INVALID, "too many points for trail ids (n + i)");
     const uint32_t cap_id_base = trails ? (uint32_t)n : 0u;
+    if (trails && !ctx->p_ext) {
+        CK(cudaMalloc((void**)&ctx->p_ext, sizeof(float4) * (size_t)ctx->max_batch * (size_t)ctx->pair_cap));
+        bin.p_ext = ctx->p_ext;
+    }
+    if (!trails) bin.p_ext = nullptr;
     const long long slots = 2 * ctx->max_points;       // survivor slots per frame: sphere + trail per point
 
     // one binning + raster pass over `np` spheres (sphere i = point i*step)
@@ -392,8 +401,10 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         LAUNCH(KID_SCAN, stream, k_scan_tiles<<<nb, 1024, 0, stream>>>(ctx->d_frames, bin, np));
         if (np > 0) {
             dim3 grid(gx, nb);
+            BinDev bin_pass = bin;
+            if (!do_trails) bin_pass.p_ext = nullptr;
             LAUNCH(KID_SCATTER, stream, k_scatter<<<grid, BIN_THREADS, use_smem ? tiles * 8 : 0, stream>>>(
-                np, ctx->d_frames, ctx->sph, ctx->rect, ctx->ext, slots, bin, use_smem, st.trail_radius));
+                np, ctx->d_frames, ctx->sph, ctx->rect, ctx->ext, slots, bin_pass, use_smem, st.trail_radius, id_base, (uint32_t)step, cap_id_base));
         }
         if (!seeded) {
             // floor keys of empty tiles, all-ones preset of split tiles
@@ -402,12 +413,13 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         }
         if (np > 0) {
             // persistent raster: CTAs pull (tile, <= ITEM_SPHERES spheres) items from per-frame queues
+            const int raster_ctas = ctx->num_sms * ctx->raster_ctas_per_sm[do_trails ? 1 : 0];
             dim3 grid((unsigned)std::max(1, std::min(raster_ctas, tiles * nb)));
             if (do_trails)
-                LAUNCH(KID_RASTER, stream, k_raster_tiles<true><<<grid, RASTER_THREADS, 0, stream>>>(
+                LAUNCH(KID_RASTER, stream, k_raster_tiles<true><<<grid, RASTER_CTA_THREADS, sizeof(RasterStage<true>) * RASTER_STAGES, stream>>>(
                     ctx->d_frames, st, ctx->sph, ctx->rect, ctx->ext, slots, bin, id_base, (uint32_t)step, cap_id_base, v, vis_stride, nb, np, seeded, (int)gx, peer));
             else
-                LAUNCH(KID_RASTER, stream, k_raster_tiles<false><<<grid, RASTER_THREADS, 0, stream>>>(
+                LAUNCH(KID_RASTER, stream, k_raster_tiles<false><<<grid, RASTER_CTA_THREADS, sizeof(RasterStage<false>) * RASTER_STAGES, stream>>>(
                     ctx->d_frames, st, ctx->sph, ctx->rect, ctx->ext, slots, bin, id_base, (uint32_t)step, 0u, v, vis_stride, nb, np, seeded, (int)gx, peer));
         }
         return PCR_OK;
@@ -487,8 +499,11 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     pcr_ctx* ctx = new (std::nothrow) pcr_ctx();
     if (!ctx) return PCR_ERR_NOMEM;
     ctx->device = device; ctx->max_points = max_points; ctx->max_w = max_w; ctx->max_h = max_h; ctx->max_batch = max_batch;
-    ctx->pair_cap = pair_capacity > 0 ? pair_capacity : 24 * max_points + 65536;
+    // a pair costs 24 bytes (40 with trails): the default leaves room for 12 tile entries per point (+ padding of
+    // every tile's range to a multiple of 4); a frame that needs more takes the unbinned raster (overflow path)
+    ctx->pair_cap = pair_capacity > 0 ? pair_capacity : 12 * max_points + 65536;
     if (ctx->pair_cap > 0xFFFFFFF0ll) ctx->pair_cap = 0xFFFFFFF0ll;
+    ctx->pair_cap = (ctx->pair_cap + 3) & ~3ll;
     ctx->tiles_cap = (((max_w + TILE - 1) / TILE) * ((max_h + TILE - 1) / TILE) + 3) & ~3;   // multiple of 4: k_scan_tiles uses uint4
     ctx->item_cap = ctx->tiles_cap + (int)(ctx->pair_cap / ITEM_SPHERES) + 1;
     {   // level 1 (8x4 pixel blocks) + level 2 (4x4 groups of them), see hiz_far_bits
@@ -510,6 +525,11 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<double, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<double, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_raster_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(RasterStage<false>) * RASTER_STAGES));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_raster_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(RasterStage<true>) * RASTER_STAGES));
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->raster_ctas_per_sm[0], k_raster_tiles<false>, RASTER_CTA_THREADS, sizeof(RasterStage<false>) * RASTER_STAGES);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->raster_ctas_per_sm[1], k_raster_tiles<true>, RASTER_CTA_THREADS, sizeof(RasterStage<true>) * RASTER_STAGES);
+        if (e == cudaSuccess && (ctx->raster_ctas_per_sm[0] < 1 || ctx->raster_ctas_per_sm[1] < 1)) e = cudaErrorLaunchOutOfResources;
     }
 #define ALLOC(ptr, bytes) if (e == cudaSuccess) e = cudaMalloc((void**)&(ptr), (bytes))
     ALLOC(ctx->sph, sizeof(float4) * B * N * 2);       // 2 survivor slots per point: its sphere and its trail
@@ -523,12 +543,14 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     ALLOC(ctx->counts, sizeof(unsigned int) * B * Tn);
     ALLOC(ctx->offsets, sizeof(unsigned int) * B * (Tn + 4));   // per-frame stride tiles_cap + 4 keeps uint4 alignment
     ALLOC(ctx->cursor, sizeof(unsigned int) * B * Tn);
-    ALLOC(ctx->pairs, sizeof(unsigned int) * B * (size_t)ctx->pair_cap);
+    ALLOC(ctx->p_sph, sizeof(float4) * B * (size_t)ctx->pair_cap);
+    ALLOC(ctx->p_cull, sizeof(unsigned int) * B * (size_t)ctx->pair_cap);
+    ALLOC(ctx->p_id, sizeof(unsigned int) * B * (size_t)ctx->pair_cap);
     ALLOC(ctx->overflow, sizeof(unsigned int) * B);
     ALLOC(ctx->stat_pairs, sizeof(unsigned long long) * (B + 16));
     ALLOC(ctx->item_count, sizeof(unsigned int) * B);
     ALLOC(ctx->item_next, sizeof(unsigned int) * B);
-    ALLOC(ctx->items, sizeof(uint2) * B * (size_t)ctx->item_cap);
+    ALLOC(ctx->items, sizeof(uint4) * B * (size_t)ctx->item_cap);
     ALLOC(ctx->hz, sizeof(unsigned int) * B * (size_t)ctx->hz_cap);
     ALLOC(ctx->d_frames, sizeof(FrameDev) * B);
 #undef ALLOC
@@ -555,7 +577,7 @@ void pcr_destroy(pcr_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     void* frees[] = {ctx->surv_count, ctx->ext, ctx->sph, ctx->rect, ctx->partials, ctx->stats, ctx->done, ctx->counts, ctx->offsets,
-                     ctx->cursor, ctx->pairs, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
+                     ctx->cursor, ctx->p_sph, ctx->p_cull, ctx->p_id, ctx->p_ext, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
                      ctx->stage_rgba[0], ctx->stage_rgba[1], ctx->stage_vis[0], ctx->stage_vis[1], ctx->stage_radius, ctx->stage_rgb,
                      ctx->peer_merged, ctx->peer_image, ctx->mesh_verts, ctx->mesh_prof, ctx->plan, ctx->dstats, ctx->dxf, ctx->dctrl, ctx->dcount};
     for (void* p : frees) if (p) cudaFree(p);
