@@ -58,7 +58,7 @@ struct pcr_ctx {
     unsigned int* done = nullptr;
     unsigned int *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *overflow = nullptr;
     float4* p_sph = nullptr;          // per (tile, primitive) pair, in tile order (K2b -> K3): centre + r^2,
-    unsigned int *p_cull = nullptr, *p_id = nullptr;   // cull word, key id,
+    uint2* p_ci = nullptr;            // cull word + key id,
     float4* p_ext = nullptr;          // capsule end B — allocated when the first frames with trails arrive
     int raster_ctas_per_sm[2] = {4, 2};   // k_raster_tiles<false / true>: resident CTAs per SM (occupancy query)
     unsigned long long* stat_pairs = nullptr;
@@ -239,7 +239,7 @@ BinDev bin_of(pcr_ctx* c)
 {
     BinDev b;
     b.counts = c->counts; b.offsets = c->offsets; b.cursor = c->cursor;
-    b.p_sph = c->p_sph; b.p_cull = c->p_cull; b.p_id = c->p_id; b.p_ext = c->p_ext;
+    b.p_sph = c->p_sph; b.p_ci = c->p_ci; b.p_ext = c->p_ext;
     b.overflow = c->overflow; b.stat_pairs = c->stat_pairs; b.tiles_cap = c->tiles_cap; b.pair_cap = c->pair_cap;
     b.item_count = c->item_count; b.item_next = c->item_next; b.items = c->items; b.item_cap = c->item_cap;
     b.surv_count = c->surv_count; b.gx_cap = c->gx_cap;
@@ -289,8 +289,11 @@ int upload_frames(pcr_ctx* ctx, const pcr_camera* cams, int nb, cudaStream_t str
 int launch_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, long long n, int cols, long long frame_stride,
                  int nb, double* partials, double* stats, int finalize, cudaStream_t stream, int mean_mode = PCR_MEAN_F64)
 {
-    int blocks = (int)std::min<long long>((n + 256 * 8 - 1) / (256 * 8), MAX_STAT_BLOCKS);
-    blocks = std::max(blocks, 1);
+    // 32 points per thread: the per-block reduction (f64 shuffles, last-block fold) must not outweigh the streaming
+    int blocks = (int)std::min<long long>((n + 256 * 32 - 1) / (256 * 32), MAX_STAT_BLOCKS);
+    if ((long long)blocks * nb < 2 * ctx->num_sms)        // few frames: keep every SM busy with smaller chunks
+        blocks = (int)std::min<long long>((n + 2047) / 2048, (2 * ctx->num_sms + nb - 1) / nb);
+    blocks = std::min(std::max(blocks, 1), MAX_STAT_BLOCKS);
     dim3 grid(blocks, nb);
     // float4 streaming needs 3 columns and every frame base on a 16-byte boundary
     const int vec = !in_is_f64 && cols == 3 && ((uintptr_t)d_in % 16 == 0) && (nb == 1 || (frame_stride * 4) % 16 == 0);
@@ -381,7 +384,7 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
     const long long slots = 2 * ctx->max_points;       // survivor slots per frame: sphere + trail per point
 
     // one binning + raster pass over `np` spheres (sphere i = point i*step)
-    auto pass = [&](long long np, int step, const unsigned int* hz, int seeded, int do_trails, const PeerDev& peer) -> int {
+    auto pass = [&](long long np, int step, const unsigned int* hz, int seeded, int do_trails, const PeerDev& peer, unsigned int* hz_out) -> int {
         unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((np + 2047) / 2048, std::max(1, 2 * resident / nb)));
         if (!use_smem) gx = (unsigned)std::max<long long>(1, (np + BIN_THREADS * 4 - 1) / (BIN_THREADS * 4));
         gx = std::min<unsigned>(gx, (unsigned)ctx->gx_cap);
@@ -409,7 +412,7 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         if (!seeded) {
             // floor keys of empty tiles, all-ones preset of split tiles
             dim3 grid((unsigned)std::max(1, std::min((tiles + 7) / 8, ctx->num_sms * 32 / nb)), nb);
-            LAUNCH(KID_FILL, stream, k_fill_tiles<<<grid, 256, 0, stream>>>(ctx->d_frames, st, bin, v, vis_stride));
+            LAUNCH(KID_FILL, stream, k_fill_tiles<<<grid, 256, 0, stream>>>(ctx->d_frames, st, bin, v, vis_stride, hz_out, ctx->hz_cap));
         }
         if (np > 0) {
             // persistent raster: CTAs pull (tile, <= ITEM_SPHERES spheres) items from per-frame queues
@@ -417,10 +420,10 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
             dim3 grid((unsigned)std::max(1, std::min(raster_ctas, tiles * nb)));
             if (do_trails)
                 LAUNCH(KID_RASTER, stream, k_raster_tiles<true><<<grid, RASTER_CTA_THREADS, sizeof(RasterStage<true>) * RASTER_STAGES, stream>>>(
-                    ctx->d_frames, st, ctx->sph, ctx->rect, ctx->ext, slots, bin, id_base, (uint32_t)step, cap_id_base, v, vis_stride, nb, np, seeded, (int)gx, peer));
+                    ctx->d_frames, st, ctx->sph, ctx->rect, ctx->ext, slots, bin, id_base, (uint32_t)step, cap_id_base, v, vis_stride, nb, np, seeded, (int)gx, peer, hz_out, ctx->hz_cap));
             else
                 LAUNCH(KID_RASTER, stream, k_raster_tiles<false><<<grid, RASTER_CTA_THREADS, sizeof(RasterStage<false>) * RASTER_STAGES, stream>>>(
-                    ctx->d_frames, st, ctx->sph, ctx->rect, ctx->ext, slots, bin, id_base, (uint32_t)step, 0u, v, vis_stride, nb, np, seeded, (int)gx, peer));
+                    ctx->d_frames, st, ctx->sph, ctx->rect, ctx->ext, slots, bin, id_base, (uint32_t)step, 0u, v, vis_stride, nb, np, seeded, (int)gx, peer, hz_out, ctx->hz_cap));
         }
         return PCR_OK;
     };
@@ -429,18 +432,18 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
     if (occl && n > ctx->occlusion_step) {
         // occluder pre-pass (every step-th point, true ids) -> Hi-Z -> main pass seeded with its keys
         const int step = ctx->occlusion_step;
-        int rc = pass((n + step - 1) / step, step, nullptr, 0, 0, no_peer);       // trails are never occluders; only the final pass pushes
+        int rc = pass((n + step - 1) / step, step, nullptr, 0, 0, no_peer, ctx->hz);       // trails are never occluders; only the final pass pushes
         if (rc) return rc;
-        const int hzn = ((W + HZ_W - 1) / HZ_W) * ((H + HZ_H - 1) / HZ_H);
-        dim3 grid((unsigned)((hzn + 255) / 256), nb);
-        LAUNCH(KID_HIZ, stream, k_hiz<<<grid, 256, 0, stream>>>(ctx->d_frames, v, vis_stride, ctx->hz, ctx->hz_cap));
+        // level-1 Hi-Z entries were written by k_fill_tiles (empty tiles) and the raster (single-item tiles)
+        dim3 grid((unsigned)((tiles + 7) / 8), nb);
+        LAUNCH(KID_HIZ, stream, k_hiz_split<<<grid, 256, 0, stream>>>(ctx->d_frames, bin, v, vis_stride, ctx->hz, ctx->hz_cap));
         const int hzn2 = (((W + HZ_W - 1) / HZ_W + 3) / 4) * (((H + HZ_H - 1) / HZ_H + 3) / 4);
         dim3 grid2((unsigned)((hzn2 + 255) / 256), nb);
         LAUNCH(KID_HIZ, stream, k_hiz2<<<grid2, 256, 0, stream>>>(ctx->d_frames, ctx->hz, ctx->hz_cap));
-        rc = pass(n, 1, ctx->hz, 1, trails, peer_final);
+        rc = pass(n, 1, ctx->hz, 1, trails, peer_final, nullptr);
         if (rc) return rc;
     } else {
-        int rc = pass(n, 1, nullptr, 0, trails, peer_final);
+        int rc = pass(n, 1, nullptr, 0, trails, peer_final, nullptr);
         if (rc) return rc;
     }
     if (rgba) return launch_shade(ctx, st, vis, vis_stride, pos, attr, in_stride, raw, n, nb, id_base, owner_only, W, H, rgba, rgba_stride, stream);
@@ -544,8 +547,7 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     ALLOC(ctx->offsets, sizeof(unsigned int) * B * (Tn + 4));   // per-frame stride tiles_cap + 4 keeps uint4 alignment
     ALLOC(ctx->cursor, sizeof(unsigned int) * B * Tn);
     ALLOC(ctx->p_sph, sizeof(float4) * B * (size_t)ctx->pair_cap);
-    ALLOC(ctx->p_cull, sizeof(unsigned int) * B * (size_t)ctx->pair_cap);
-    ALLOC(ctx->p_id, sizeof(unsigned int) * B * (size_t)ctx->pair_cap);
+    ALLOC(ctx->p_ci, sizeof(uint2) * B * (size_t)ctx->pair_cap);
     ALLOC(ctx->overflow, sizeof(unsigned int) * B);
     ALLOC(ctx->stat_pairs, sizeof(unsigned long long) * (B + 16));
     ALLOC(ctx->item_count, sizeof(unsigned int) * B);
@@ -577,7 +579,7 @@ void pcr_destroy(pcr_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     void* frees[] = {ctx->surv_count, ctx->ext, ctx->sph, ctx->rect, ctx->partials, ctx->stats, ctx->done, ctx->counts, ctx->offsets,
-                     ctx->cursor, ctx->p_sph, ctx->p_cull, ctx->p_id, ctx->p_ext, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
+                     ctx->cursor, ctx->p_sph, ctx->p_ci, ctx->p_ext, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
                      ctx->stage_rgba[0], ctx->stage_rgba[1], ctx->stage_vis[0], ctx->stage_vis[1], ctx->stage_radius, ctx->stage_rgb,
                      ctx->peer_merged, ctx->peer_image, ctx->mesh_verts, ctx->mesh_prof, ctx->plan, ctx->dstats, ctx->dxf, ctx->dctrl, ctx->dcount};
     for (void* p : frees) if (p) cudaFree(p);
