@@ -348,6 +348,13 @@ int pcr_profile(pcr_ctx* ctx, int enable);
 int pcr_profile_read(pcr_ctx* ctx, double* ms_out, int64_t* count_out, int capacity);
 const char* pcr_kernel_name(int kernel_id);
 
+/* Diagnostics.  The standardisation (p - centre) / scale divides every coordinate of a frame by one scale; the
+ * kernels hoist the reciprocal refinement of the hardware's IEEE division sequence out of the per-point loop
+ * (scale_div in pcr_kernels.cuh).  This entry checks that shortcut against __fdiv_rn for EVERY binary32 dividend and
+ * each of the n given divisors (host array) and writes the number of differing quotient bit patterns (expected 0).
+ * Synchronous. */
+int pcr_selftest_scale_div(pcr_ctx* ctx, const float* h_divisors, int n, uint64_t* mismatches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,7 +27,7 @@ SYMBOLS = (
     "pcr_transform_coordinates", "pcr_profile", "pcr_profile_read", "pcr_kernel_name", "pcr_set_occlusion", "pcr_finalize_stats", "pcr_velocity_trails", "pcr_render_shard", "pcr_shade_shard",
     "pcr_set_droplet_mesh", "pcr_droplet_transforms", "pcr_history_trails", "pcr_render_droplet_frames",
     "pcr_peer_alloc", "pcr_ipc_export", "pcr_ipc_open", "pcr_ipc_close", "pcr_peer_set", "pcr_peer_begin_frame",
-    "pcr_render_shard_peer", "pcr_shade_shard_peer",
+    "pcr_render_shard_peer", "pcr_shade_shard_peer", "pcr_selftest_scale_div",
 )
 HISTORY_FRAMES, MAX_CTRL = 20, 21                   # PCR_HISTORY_FRAMES, PCR_MAX_CTRL
 TRAILS_NONE, TRAILS_VELOCITY, TRAILS_HISTORY = 0, 1, 2
@@ -91,6 +91,7 @@ def load_library():
     L.pcr_stats_partial.argtypes = [vp, vp, i32, i64, i32, vp, vp]
     L.pcr_standardize_with_stats.argtypes = [vp, vp, i32, i64, i32, vp, vp, styp, vp, vp, vp, vp, vp]
     L.pcr_counters.argtypes = [vp, ctypes.POINTER(i64), vp]
+    L.pcr_selftest_scale_div.argtypes = [vp, ctypes.POINTER(ctypes.c_float), i32, ctypes.POINTER(ctypes.c_uint64)]
     L.pcr_transform_coordinates.argtypes = [vp, vp, i64, i32, i32, ctypes.c_float, vp, vp]
     L.pcr_set_occlusion.argtypes = [vp, i32, i32, i64]
     L.pcr_finalize_stats.argtypes = [vp, vp, i32, i64, i32, vp, vp]
@@ -476,6 +477,14 @@ class Context:
         out = (ctypes.c_int64 * 4)()
         self._check(self.lib.pcr_counters(self.handle, out, _stream_ptr(stream)))
         return {"launches": out[0], "pairs_last_frame": out[1], "overflow_frames": out[2]}
+
+    def selftest_scale_div(self, divisors):
+        """Mismatching quotient bit patterns between the kernels' hoisted-reciprocal division and __fdiv_rn over
+        every binary32 dividend, for each given divisor (expected 0)."""
+        d = (ctypes.c_float * len(divisors))(*[float(x) for x in divisors])
+        bad = ctypes.c_uint64(0)
+        self._check(self.lib.pcr_selftest_scale_div(self.handle, d, len(divisors), ctypes.byref(bad)))
+        return int(bad.value)
 
 
 def _device_view(ptr, shape, dtype, device):

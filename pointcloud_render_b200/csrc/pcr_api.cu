@@ -1393,6 +1393,30 @@ int pcr_shade_shard_peer(pcr_ctx* ctx, const uint64_t* d_vis, const void* d_in, 
     return leave(ctx, s);
 }
 
+int pcr_selftest_scale_div(pcr_ctx* ctx, const float* h_divisors, int n, uint64_t* mismatches)
+{
+    if (!ctx) return PCR_ERR_INVALID;
+    if (!h_divisors || !mismatches || n < 1 || n > 65535) return fail(ctx, PCR_ERR_INVALID, "divisors / mismatches NULL or n out of range");
+    CK(cudaSetDevice(ctx->device));
+    float* d_div = nullptr;
+    unsigned long long* d_bad = nullptr;
+    CK(cudaMalloc((void**)&d_div, sizeof(float) * n));
+    cudaError_t e = cudaMalloc((void**)&d_bad, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemcpy(d_div, h_divisors, sizeof(float) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d_bad, 0, sizeof(unsigned long long));
+    if (e == cudaSuccess) {
+        k_selftest_scale_div<<<dim3((unsigned)(ctx->num_sms * 8), (unsigned)n), 256>>>(d_div, n, d_bad);
+        e = cudaGetLastError();
+    }
+    unsigned long long bad = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
+    cudaFree(d_div);
+    if (d_bad) cudaFree(d_bad);
+    if (e != cudaSuccess) return fail(ctx, PCR_ERR_CUDA, "pcr_selftest_scale_div", e);
+    *mismatches = bad;
+    return PCR_OK;
+}
+
 const char* pcr_kernel_name(int kernel_id) { return kernel_id >= 0 && kernel_id < KID_COUNT ? kKernelNames[kernel_id] : ""; }
 
 }  // extern "C"

@@ -581,3 +581,15 @@ def test_zero_frames_and_tiny_inputs(ctx):
     rgba, vis = ctx.render_frames(one, [cfg.camera(0, 220, 64, 48)], cfg.style(), want_vis=True)
     ids = _native.keys_to_ids(vis)
     assert np.all(ids >= 0xFFFFFFFE)                                      # nothing but floor / miss
+
+
+def test_hoisted_scale_division_is_ieee_exact(ctx):
+    """K1 divides every coordinate of a frame by one scale; the kernels reuse the scale's refined reciprocal
+    (scale_div, pcr_kernels.cuh).  Exhaustive check: every binary32 dividend x a spread of divisors (typical cloud
+    extents, powers of two, all-ones mantissas, both ends of the fast range and beyond it) must give the bit
+    pattern of __fdiv_rn."""
+    rng = np.random.default_rng(7)
+    divisors = list(np.exp(rng.uniform(np.log(1e-3), np.log(1e4), 40)).astype(np.float32))
+    divisors += [1.0, 2.0, 0.5, 3.0, 1.9999999, 1.0000001, 0.99999994, 7.9999995, 2.0 ** -40, 2.0 ** 40, 2.0 ** -41, 2.0 ** 41,
+                 1e-30, 1e30, 1.1754944e-38, 3.4028235e38]
+    assert ctx.selftest_scale_div(divisors) == 0
