@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--workload", default="H", choices=["H", "C2", "C3", "C4", "C5", "C2D", "C4D"])
     ap.add_argument("--points", type=int, default=0, help="override the workload's point count (C5 scaling studies)")
     ap.add_argument("--frames-per-step", type=int, default=0, help="frames per step per GPU (0 = workload default)")
+    ap.add_argument("--max-batch", type=int, default=16, help="frames per internal launch (pcr_create max_batch, <= 64)")
     ap.add_argument("--ring", type=int, default=0, help="resident frames per GPU (0 = enough to exceed L2)")
     ap.add_argument("--trails", action="store_true", help="also draw the reference's velocity trails (6-column workloads C3/C4)")
     ap.add_argument("--merge", default="fused", choices=["fused", "nccl"],
@@ -404,7 +405,7 @@ def run_droplets(args, spec, rank, world, local_rank):
     host_np = moving_trajectory(halo + 2 * B, n, seed=rank)
     host = torch.from_numpy(host_np).pin_memory()
     resident = host.cuda()
-    ctx = _native.Context(device=local_rank, max_points=n, max_w=W, max_h=H, max_batch=min(B, 16))
+    ctx = _native.Context(device=local_rank, max_points=n, max_w=W, max_h=H, max_batch=min(B, args.max_batch))
     ctx.set_droplet_mesh(droplets.droplet_vertices(), droplets.N_RINGS, droplets.N_SEGMENTS)
     style = cfg.style(color_mode=0, trails=trails if trails == 2 else True)
     first = spec["frames"] // 2
@@ -547,7 +548,7 @@ def main():
     resident = host.cuda(non_blocking=True)
     radius_np = synthetic.radii(n) if spec["radii"] else None
     radius = torch.from_numpy(radius_np).cuda() if radius_np is not None else None
-    ctx = _native.Context(device=local_rank, max_points=n, max_w=W, max_h=H, max_batch=min(B, 16))
+    ctx = _native.Context(device=local_rank, max_points=n, max_w=W, max_h=H, max_batch=min(B, args.max_batch))
     cams_all, cfg = cameras_for(spec, rank * 1000, ring)
     style = cfg.style(color_mode=spec["color_mode"], trails=args.trails and spec["cols"] == 6)
     rgba = torch.empty((B, H, W, 4), dtype=torch.uint8, device="cuda")

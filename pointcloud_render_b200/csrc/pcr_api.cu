@@ -72,6 +72,7 @@ struct pcr_ctx {
     unsigned int* hz = nullptr;       // [max_batch][hz_cap] farthest pre-pass depth per 8x4 pixel block
     int hz_cap = 0;
     int occlusion = -1;               // -1 auto (n >= occlusion_min_points), 0 off, 1 always
+    int two_phase = 1;                // K2a's coarse-then-fine Hi-Z cull (PCR_TWO_PHASE=0 disables: diagnostics)
     int occlusion_step = 16;          // the pre-pass rasterises every step-th point
     long long occlusion_min_points = 1 << 17;
     uint64_t* vis = nullptr;          // lazily allocated when the caller passes d_vis == NULL
@@ -390,10 +391,15 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         gx = std::min<unsigned>(gx, (unsigned)ctx->gx_cap);
         if (np > 0) {
             dim3 grid(gx, nb);
-            const size_t sm = use_smem ? (size_t)tiles * 4 : 0;
+            // two-phase cull (see k_project_count): main pass over a Hi-Z, tile histogram + coarse Hi-Z level + the
+            // warps' rings must fit in shared memory
+            const int hz_w1 = (W + HZ_W - 1) / HZ_W, hz_h1 = (H + HZ_H - 1) / HZ_H;
+            const size_t sm2 = (size_t)tiles * 4 + (size_t)((hz_w1 + 3) / 4) * ((hz_h1 + 3) / 4) * 4 + (size_t)(BIN_THREADS / 32) * 5 * RING_CAP * 4;
+            const int two_phase = (ctx->two_phase && hz && use_smem && !do_trails && sm2 <= (size_t)ctx->smem_optin / 2) ? 1 : 0;
+            const size_t sm = two_phase ? sm2 : (use_smem ? (size_t)tiles * 4 : 0);
 #define PCR_PROJECT(T, RAWB, TRB, posarg, strarg, rawarg)                                                                        \
     LAUNCH(KID_PROJECT, stream, (k_project_count<T, RAWB, TRB><<<grid, BIN_THREADS, sm, stream>>>(                               \
-        posarg, np, strarg, rawarg, st, step, ctx->d_frames, ctx->sph, ctx->rect, ctx->ext, slots, bin, use_smem, hz, ctx->hz_cap)))
+        posarg, np, strarg, rawarg, st, step, ctx->d_frames, ctx->sph, ctx->rect, ctx->ext, slots, bin, use_smem, hz, ctx->hz_cap, two_phase)))
             if (!raw) PCR_PROJECT(float, false, false, pos, in_stride, raw_frames<float>(nullptr));
             else if (raw->is_f64 && do_trails) PCR_PROJECT(double, true, true, nullptr, 0, raw_frames<double>(raw));
             else if (raw->is_f64) PCR_PROJECT(double, true, false, nullptr, 0, raw_frames<double>(raw));
@@ -514,6 +520,7 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
         ctx->hz_cap = w1 * h1 + ((w1 + 3) / 4) * ((h1 + 3) / 4);
     }
     if (const char* e = getenv("PCR_OCCLUSION")) ctx->occlusion = atoi(e);
+    if (const char* e = getenv("PCR_TWO_PHASE")) ctx->two_phase = atoi(e);
     if (const char* e = getenv("PCR_OCCLUSION_STEP")) ctx->occlusion_step = std::max(2, atoi(e));
     const size_t B = (size_t)max_batch, N = (size_t)max_points, Tn = (size_t)ctx->tiles_cap;
     cudaError_t e = cudaSetDevice(device);
