@@ -72,6 +72,7 @@ struct pcr_ctx {
     unsigned int* hz = nullptr;       // [max_batch][hz_cap] farthest pre-pass depth per 8x4 pixel block
     int hz_cap = 0;
     int occlusion = -1;               // -1 auto (n >= occlusion_min_points), 0 off, 1 always
+    int scatter_threads = BIN_THREADS; // K2b threads per chunk (PCR_SCATTER_THREADS: diagnostics)
     int two_phase = 1;                // K2a's coarse-then-fine Hi-Z cull (PCR_TWO_PHASE=0 disables: diagnostics)
     int occlusion_step = 16;          // the pre-pass rasterises every step-th point
     long long occlusion_min_points = 1 << 17;
@@ -412,7 +413,7 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
             dim3 grid(gx, nb);
             BinDev bin_pass = bin;
             if (!do_trails) bin_pass.p_ext = nullptr;
-            LAUNCH(KID_SCATTER, stream, k_scatter<<<grid, BIN_THREADS, use_smem ? tiles * 8 : 0, stream>>>(
+            LAUNCH(KID_SCATTER, stream, k_scatter<<<grid, ctx->scatter_threads, use_smem ? tiles * 8 : 0, stream>>>(
                 np, ctx->d_frames, ctx->sph, ctx->rect, ctx->ext, slots, bin_pass, use_smem, st.trail_radius, id_base, (uint32_t)step, cap_id_base));
         }
         if (!seeded) {
@@ -521,6 +522,7 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     }
     if (const char* e = getenv("PCR_OCCLUSION")) ctx->occlusion = atoi(e);
     if (const char* e = getenv("PCR_TWO_PHASE")) ctx->two_phase = atoi(e);
+    if (const char* e = getenv("PCR_SCATTER_THREADS")) ctx->scatter_threads = std::min(BIN_THREADS, std::max(32, atoi(e) & ~31));
     if (const char* e = getenv("PCR_OCCLUSION_STEP")) ctx->occlusion_step = std::max(2, atoi(e));
     const size_t B = (size_t)max_batch, N = (size_t)max_points, Tn = (size_t)ctx->tiles_cap;
     cudaError_t e = cudaSetDevice(device);
