@@ -145,8 +145,8 @@ int pcr_abi_version(void);
 
 /* Allocates scratch for up to max_points points per frame, max_w x max_h pixels and
  * max_batch frames in flight per launch.  pair_capacity = max (tile, sphere) pairs per
- * frame (0 = default 12*max_points + 65536; 24 bytes of scratch each, 40 once frames with
- * trails are rendered); frames that exceed it take the slower un-binned raster, results are
+ * frame (0 = default 24*max_points + 65536 up to 262144 points, 12*max_points + 65536 above;
+ * 24 bytes of scratch each, 40 once frames with trails are rendered); frames that exceed it take the slower un-binned raster, results are
  * identical.  Synchronous. */
 int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max_h,
                int max_batch, int64_t pair_capacity);

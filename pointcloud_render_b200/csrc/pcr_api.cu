@@ -509,9 +509,10 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     pcr_ctx* ctx = new (std::nothrow) pcr_ctx();
     if (!ctx) return PCR_ERR_NOMEM;
     ctx->device = device; ctx->max_points = max_points; ctx->max_w = max_w; ctx->max_h = max_h; ctx->max_batch = max_batch;
-    // a pair costs 24 bytes (40 with trails): the default leaves room for 12 tile entries per point (+ padding of
-    // every tile's range to a multiple of 4); a frame that needs more takes the unbinned raster (overflow path)
-    ctx->pair_cap = pair_capacity > 0 ? pair_capacity : 12 * max_points + 65536;
+    // a pair costs 24 bytes (40 with trails): the default leaves room for 24 tile entries per point up to 262144
+    // points (trails cross many tiles), 12 above (+ padding of every tile's range to a multiple of 4); a frame that
+    // needs more takes the unbinned raster (overflow path)
+    ctx->pair_cap = pair_capacity > 0 ? pair_capacity : (max_points <= 262144 ? 24 : 12) * max_points + 65536;
     if (ctx->pair_cap > 0xFFFFFFF0ll) ctx->pair_cap = 0xFFFFFFF0ll;
     ctx->pair_cap = (ctx->pair_cap + 3) & ~3ll;
     ctx->tiles_cap = (((max_w + TILE - 1) / TILE) * ((max_h + TILE - 1) / TILE) + 3) & ~3;   // multiple of 4: k_scan_tiles uses uint4
