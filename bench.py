@@ -669,6 +669,7 @@ def main():
                     "algorithmic_bytes_per_launch": bytes_per_launch, "frames_per_launch": frames_per_launch,
                     "us_per_launch": top_ms / top_cnt * 1e3, "launches_per_step": launches_per_step,
                     "whole_step_achieved_gbs": spec["algorithmic_bytes_per_frame"] * B * args.steps / (dev_ms * 1e-3) / 1e9,
+                    "whole_step_frac": spec["algorithmic_bytes_per_frame"] * B * args.steps / (dev_ms * 1e-3) / 1e9 / peak,
                     "note": "algorithmic bytes = N*b_in + W*H*(8+4) per frame (SURVEY.md 8d); the path is bound by sphere-pixel "
                             "tests, not by HBM bytes"}
 
