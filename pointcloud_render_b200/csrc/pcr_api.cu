@@ -413,8 +413,12 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
             dim3 grid(gx, nb);
             BinDev bin_pass = bin;
             if (!do_trails) bin_pass.p_ext = nullptr;
-            LAUNCH(KID_SCATTER, stream, k_scatter<<<grid, ctx->scatter_threads, use_smem ? tiles * 8 : 0, stream>>>(
-                np, ctx->d_frames, ctx->sph, ctx->rect, ctx->ext, slots, bin_pass, use_smem, st.trail_radius, id_base, (uint32_t)step, cap_id_base));
+            if (do_trails)
+                LAUNCH(KID_SCATTER, stream, k_scatter<true><<<grid, ctx->scatter_threads, use_smem ? tiles * 8 : 0, stream>>>(
+                    np, ctx->d_frames, ctx->sph, ctx->rect, ctx->ext, slots, bin_pass, use_smem, st.trail_radius, id_base, (uint32_t)step, cap_id_base));
+            else
+                LAUNCH(KID_SCATTER, stream, k_scatter<false><<<grid, ctx->scatter_threads, use_smem ? tiles * 8 : 0, stream>>>(
+                    np, ctx->d_frames, ctx->sph, ctx->rect, ctx->ext, slots, bin_pass, use_smem, st.trail_radius, id_base, (uint32_t)step, cap_id_base));
         }
         if (!seeded) {
             // floor keys of empty tiles, all-ones preset of split tiles
@@ -537,7 +541,8 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<float, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<double, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<double, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_raster_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(RasterStage<false>) * RASTER_STAGES));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_raster_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(RasterStage<true>) * RASTER_STAGES));
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->raster_ctas_per_sm[0], k_raster_tiles<false>, RASTER_CTA_THREADS, sizeof(RasterStage<false>) * RASTER_STAGES);
