@@ -26,12 +26,12 @@ constexpr int MAX_STAT_BLOCKS = 1184;   // 148 SMs x 8
 
 enum KernelId { KID_STATS = 0, KID_TRANSFORM, KID_PROJECT, KID_SCAN, KID_SCATTER, KID_RASTER, KID_HIZ, KID_SHADE,
                 KID_ZMIN, KID_AXIS, KID_FILL, KID_MEAN, KID_LUT, KID_DROP_PREP, KID_FILL_FLOOR, KID_RASTER_POLY, KID_RASTER_DROP,
-                KID_SHADE_DROP, KID_PEER_INIT, KID_SHADE_PEER, KID_COUNT };
+                KID_SHADE_DROP, KID_PEER_INIT, KID_SHADE_PEER, KID_SHADE_FLOOR, KID_COUNT };
 const char* const kKernelNames[KID_COUNT] = {"k_stats", "k_transform", "k_project_count", "k_scan_tiles", "k_scatter",
                                              "k_raster_tiles", "k_hiz", "k_shade", "k_zmin", "k_axis_transform",
                                              "k_fill_tiles", "k_mean_sequential", "k_build_floor_lut", "k_droplet_prepare",
                                              "k_fill_floor", "k_raster_polylines", "k_raster_droplets", "k_shade_droplets", "k_peer_init_rows",
-                                             "k_shade_peer"};
+                                             "k_shade_peer", "k_shade_floor_tiles"};
 constexpr size_t PROF_MAX_RECORDS = 1 << 16;
 
 struct ProfRec { int kid; cudaEvent_t a, b; };
@@ -59,6 +59,8 @@ struct pcr_ctx {
     unsigned int *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *overflow = nullptr;
     float4* p_sph = nullptr;          // per (tile, primitive) pair, in tile order (K2b -> K3): centre + r^2,
     uint2* p_ci = nullptr;            // cull word + key id,
+    unsigned int* tile_state = nullptr;   // [max_batch][tiles_cap] lazy floor fill (BinDev::tile_state)
+    int lazy_fill = 1;                // PCR_LAZY_FILL=0 disables (diagnostics)
     float4* p_ext = nullptr;          // capsule end B — allocated when the first frames with trails arrive
     int raster_ctas_per_sm[2] = {4, 2};   // k_raster_tiles<false / true>: resident CTAs per SM (occupancy query)
     unsigned long long* stat_pairs = nullptr;
@@ -241,7 +243,7 @@ BinDev bin_of(pcr_ctx* c)
 {
     BinDev b;
     b.counts = c->counts; b.offsets = c->offsets; b.cursor = c->cursor;
-    b.p_sph = c->p_sph; b.p_ci = c->p_ci; b.p_ext = c->p_ext;
+    b.p_sph = c->p_sph; b.p_ci = c->p_ci; b.p_ext = c->p_ext; b.tile_state = nullptr;
     b.overflow = c->overflow; b.stat_pairs = c->stat_pairs; b.tiles_cap = c->tiles_cap; b.pair_cap = c->pair_cap;
     b.item_count = c->item_count; b.item_next = c->item_next; b.items = c->items; b.item_cap = c->item_cap;
     b.surv_count = c->surv_count; b.gx_cap = c->gx_cap;
@@ -341,23 +343,35 @@ RawFrames<T> raw_frames(const RawSrc* r)
     return f;
 }
 
-int launch_shade(pcr_ctx* ctx, const StyleDev& st, const uint64_t* vis, long long vis_stride, const float4* pos, const float4* attr,
+int launch_shade(pcr_ctx* ctx, const StyleDev& st, const uint64_t* vis_in, long long vis_stride, const float4* pos, const float4* attr,
                  long long in_stride, const RawSrc* raw, long long n, int nb, uint32_t id_base, int owner_only, int W, int H,
-                 uint8_t* rgba, long long rgba_stride, cudaStream_t stream)
+                 uint8_t* rgba, long long rgba_stride, cudaStream_t stream, const unsigned int* tile_state = nullptr)
 {
+    uint64_t* vis = const_cast<uint64_t*>(vis_in);      // written only where tile_state says the keys do not exist yet
+    const int tiles_cap = ctx->tiles_cap;
     FloorLut lut;
     int rc = floor_lut(ctx, st, stream, &lut);
     if (rc) return rc;
     dim3 grid((unsigned)((W + 63) / 64), (unsigned)((H + 4 * SHADE_ROWS - 1) / (4 * SHADE_ROWS)), nb);
+    if (tile_state) {
+        // the tiles nothing was drawn in: keys + ground shading in one go; k_shade takes the others from a list
+        const int tiles = ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+        LAUNCH(KID_SHADE_FLOOR, stream, k_active_tiles<<<nb, 1024, 0, stream>>>(ctx->d_frames, ctx->tile_state, tiles_cap));
+        grid = dim3((unsigned)std::max(1, std::min((tiles + 3) / 4, 2 * ctx->num_sms * 4 / nb + 1)), 1, nb);
+        dim3 fgrid((unsigned)std::max(1, std::min((tiles + 7) / 8, ctx->num_sms * 32 / nb)), nb);
+        LAUNCH(KID_SHADE_FLOOR, stream, k_shade_floor_tiles<<<fgrid, 256, 0, stream>>>(ctx->d_frames, st, lut, tile_state, tiles_cap,
+                                                                                     (unsigned long long*)vis, vis_stride, (uint32_t*)rgba, rgba_stride,
+                                                                                     owner_only && id_base != 0 ? 1 : 0));
+    }
     if (!raw)
         LAUNCH(KID_SHADE, stream, k_shade<float, false><<<grid, 256, 0, stream>>>(ctx->d_frames, st, lut, vis, vis_stride, pos, attr, in_stride,
-                                                                                 raw_frames<float>(nullptr), n, id_base, owner_only, (uint32_t*)rgba, rgba_stride));
+                                                                                 raw_frames<float>(nullptr), n, id_base, owner_only, (uint32_t*)rgba, rgba_stride, tile_state, tiles_cap));
     else if (raw->is_f64)
         LAUNCH(KID_SHADE, stream, k_shade<double, true><<<grid, 256, 0, stream>>>(ctx->d_frames, st, lut, vis, vis_stride, nullptr, nullptr, 0,
-                                                                                 raw_frames<double>(raw), n, id_base, owner_only, (uint32_t*)rgba, rgba_stride));
+                                                                                 raw_frames<double>(raw), n, id_base, owner_only, (uint32_t*)rgba, rgba_stride, tile_state, tiles_cap));
     else
         LAUNCH(KID_SHADE, stream, k_shade<float, true><<<grid, 256, 0, stream>>>(ctx->d_frames, st, lut, vis, vis_stride, nullptr, nullptr, 0,
-                                                                                raw_frames<float>(raw), n, id_base, owner_only, (uint32_t*)rgba, rgba_stride));
+                                                                                raw_frames<float>(raw), n, id_base, owner_only, (uint32_t*)rgba, rgba_stride, tile_state, tiles_cap));
     return PCR_OK;
 }
 
@@ -378,6 +392,9 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
     const int trails = raw && st.trails == 1 && raw->cols == 6 ? 1 : 0;
     if (trails && 2 * (unsigned long long)n > 0xFFFFFFF0ull) return fail(ctx, PCR_ERR_INVALID, "too many points for trail ids (n + i)");
     const uint32_t cap_id_base = trails ? (uint32_t)n : 0u;
+    // lazy floor fill: tiles in which nothing is drawn get their keys from K4 — only when K4 follows in this very call
+    const bool lazy = ctx->lazy_fill && rgba != nullptr && push == nullptr;
+    if (lazy) bin.tile_state = ctx->tile_state;
     if (trails && !ctx->p_ext) {
         CK(cudaMalloc((void**)&ctx->p_ext, sizeof(float4) * (size_t)ctx->max_batch * (size_t)ctx->pair_cap));
         bin.p_ext = ctx->p_ext;
@@ -408,7 +425,12 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
             else PCR_PROJECT(float, true, false, nullptr, 0, raw_frames<float>(raw));
 #undef PCR_PROJECT
         }
-        LAUNCH(KID_SCAN, stream, k_scan_tiles<<<nb, 1024, 0, stream>>>(ctx->d_frames, bin, np));
+        LAUNCH(KID_SCAN, stream, k_scan_tiles<<<nb, 1024, 0, stream>>>(ctx->d_frames, bin, np, lazy ? (seeded ? 2 : 1) : 0));
+        if (lazy && seeded) {
+            // tiles only the main pass touches need the floor keys the raster starts from
+            dim3 grid((unsigned)std::max(1, std::min((tiles + 7) / 8, ctx->num_sms * 32 / nb)), nb);
+            LAUNCH(KID_FILL, stream, k_fill_tiles<<<grid, 256, 0, stream>>>(ctx->d_frames, st, bin, v, vis_stride, nullptr, ctx->hz_cap, 2));
+        }
         if (np > 0) {
             dim3 grid(gx, nb);
             BinDev bin_pass = bin;
@@ -423,7 +445,7 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         if (!seeded) {
             // floor keys of empty tiles, all-ones preset of split tiles
             dim3 grid((unsigned)std::max(1, std::min((tiles + 7) / 8, ctx->num_sms * 32 / nb)), nb);
-            LAUNCH(KID_FILL, stream, k_fill_tiles<<<grid, 256, 0, stream>>>(ctx->d_frames, st, bin, v, vis_stride, hz_out, ctx->hz_cap));
+            LAUNCH(KID_FILL, stream, k_fill_tiles<<<grid, 256, 0, stream>>>(ctx->d_frames, st, bin, v, vis_stride, hz_out, ctx->hz_cap, lazy ? 1 : 0));
         }
         if (np > 0) {
             // persistent raster: CTAs pull (tile, <= ITEM_SPHERES spheres) items from per-frame queues
@@ -457,7 +479,8 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         int rc = pass(n, 1, nullptr, 0, trails, peer_final, nullptr);
         if (rc) return rc;
     }
-    if (rgba) return launch_shade(ctx, st, vis, vis_stride, pos, attr, in_stride, raw, n, nb, id_base, owner_only, W, H, rgba, rgba_stride, stream);
+    if (rgba) return launch_shade(ctx, st, vis, vis_stride, pos, attr, in_stride, raw, n, nb, id_base, owner_only, W, H, rgba, rgba_stride, stream,
+                                  lazy ? ctx->tile_state : nullptr);
     return PCR_OK;
 }
 
@@ -527,6 +550,7 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     }
     if (const char* e = getenv("PCR_OCCLUSION")) ctx->occlusion = atoi(e);
     if (const char* e = getenv("PCR_TWO_PHASE")) ctx->two_phase = atoi(e);
+    if (const char* e = getenv("PCR_LAZY_FILL")) ctx->lazy_fill = atoi(e);
     if (const char* e = getenv("PCR_SCATTER_THREADS")) ctx->scatter_threads = std::min(BIN_THREADS, std::max(32, atoi(e) & ~31));
     if (const char* e = getenv("PCR_OCCLUSION_STEP")) ctx->occlusion_step = std::max(2, atoi(e));
     const size_t B = (size_t)max_batch, N = (size_t)max_points, Tn = (size_t)ctx->tiles_cap;
@@ -561,6 +585,7 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     ALLOC(ctx->counts, sizeof(unsigned int) * B * Tn);
     ALLOC(ctx->offsets, sizeof(unsigned int) * B * (Tn + 4));   // per-frame stride tiles_cap + 4 keeps uint4 alignment
     ALLOC(ctx->cursor, sizeof(unsigned int) * B * Tn);
+    ALLOC(ctx->tile_state, sizeof(unsigned int) * (2 * B * Tn + B));     // [state | active list | active count]
     ALLOC(ctx->p_sph, sizeof(float4) * B * (size_t)ctx->pair_cap);
     ALLOC(ctx->p_ci, sizeof(uint2) * B * (size_t)ctx->pair_cap);
     ALLOC(ctx->overflow, sizeof(unsigned int) * B);
@@ -594,7 +619,7 @@ void pcr_destroy(pcr_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     void* frees[] = {ctx->surv_count, ctx->ext, ctx->sph, ctx->rect, ctx->partials, ctx->stats, ctx->done, ctx->counts, ctx->offsets,
-                     ctx->cursor, ctx->p_sph, ctx->p_ci, ctx->p_ext, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
+                     ctx->cursor, ctx->p_sph, ctx->p_ci, ctx->p_ext, ctx->tile_state, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
                      ctx->stage_rgba[0], ctx->stage_rgba[1], ctx->stage_vis[0], ctx->stage_vis[1], ctx->stage_radius, ctx->stage_rgb,
                      ctx->peer_merged, ctx->peer_image, ctx->mesh_verts, ctx->mesh_prof, ctx->plan, ctx->dstats, ctx->dxf, ctx->dctrl, ctx->dcount};
     for (void* p : frees) if (p) cudaFree(p);
