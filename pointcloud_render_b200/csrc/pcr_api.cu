@@ -930,10 +930,14 @@ int pcr_render_frames_host(pcr_ctx* ctx, const void* h_in, int in_is_f64, int64_
     if (h_rgb) { CK(cudaMemcpyAsync(ctx->stage_rgb, h_rgb, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->s_comp)); d_rgb = ctx->stage_rgb; }
     // chunks of at most B frames, but at least ~8 chunks per call so that the H2D copy of chunk
     // k+1, the kernels of chunk k and the D2H copy of chunk k-1 overlap even for short calls
+    // The call's time is the H2D stream's (it is busy from the first byte to the last) plus what is left to do after
+    // the last input chunk has arrived — its kernels and its D2H copy.  So the tail of the call is cut into ever
+    // smaller chunks (C, ..., C, C/2, C/4, ..., 1).
     const int C = std::max(1, std::min(B, (n_frames + 7) / 8));
     int chunk = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += C, ++chunk) {
-        const int nb = std::min(C, n_frames - f0);
+    for (int f0 = 0, nb = 0; f0 < n_frames; f0 += nb, ++chunk) {
+        const int left = n_frames - f0;
+        nb = left > C ? C : std::max(1, left / 2);
         const int k = chunk & 1;
         if (chunk >= 2) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[k], 0));   // input slot free again
         CK(cudaMemcpyAsync(ctx->stage_in[k], (const char*)h_in + (size_t)f0 * frame_bytes, (size_t)nb * frame_bytes,
