@@ -61,6 +61,9 @@ struct pcr_ctx {
     uint2* p_ci = nullptr;            // cull word + key id,
     unsigned int* tile_state = nullptr;   // [max_batch][tiles_cap] lazy floor fill (BinDev::tile_state)
     int lazy_fill = 1;                // PCR_LAZY_FILL=0 disables (diagnostics)
+    void* sample = nullptr;           // [2][max_batch][ceil(n/step)][3] every step-th point of a frame, written by K0 for the pre-pass
+    size_t sample_bytes = 0;
+    int sample_prepass = 1;           // PCR_SAMPLE_PREPASS=0 disables (diagnostics)
     float4* p_ext = nullptr;          // capsule end B — allocated when the first frames with trails arrive
     int raster_ctas_per_sm[2] = {4, 2};   // k_raster_tiles<false / true>: resident CTAs per SM (occupancy query)
     unsigned long long* stat_pairs = nullptr;
@@ -291,7 +294,8 @@ int upload_frames(pcr_ctx* ctx, const pcr_camera* cams, int nb, cudaStream_t str
 }
 
 int launch_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, long long n, int cols, long long frame_stride,
-                 int nb, double* partials, double* stats, int finalize, cudaStream_t stream, int mean_mode = PCR_MEAN_F64)
+                 int nb, double* partials, double* stats, int finalize, cudaStream_t stream, int mean_mode = PCR_MEAN_F64,
+                 void* sample = nullptr, long long sample_stride = 0, int sample_step = 1)
 {
     // 32 points per thread: the per-block reduction (f64 shuffles, last-block fold) must not outweigh the streaming
     int blocks = (int)std::min<long long>((n + 256 * 32 - 1) / (256 * 32), MAX_STAT_BLOCKS);
@@ -302,9 +306,11 @@ int launch_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, long long n, int
     // float4 streaming needs 3 columns and every frame base on a 16-byte boundary
     const int vec = !in_is_f64 && cols == 3 && ((uintptr_t)d_in % 16 == 0) && (nb == 1 || (frame_stride * 4) % 16 == 0);
     if (in_is_f64)
-        LAUNCH(KID_STATS, stream, k_stats<double><<<grid, 256, 0, stream>>>((const double*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, ctx->done, finalize, 0));
+        LAUNCH(KID_STATS, stream, k_stats<double><<<grid, 256, 0, stream>>>((const double*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, ctx->done, finalize, 0,
+                                                                        (double*)sample, sample_stride, (unsigned int)sample_step));
     else
-        LAUNCH(KID_STATS, stream, k_stats<float><<<grid, 256, 0, stream>>>((const float*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, ctx->done, finalize, vec));
+        LAUNCH(KID_STATS, stream, k_stats<float><<<grid, 256, 0, stream>>>((const float*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, ctx->done, finalize, vec,
+                                                                       (float*)sample, sample_stride, (unsigned int)sample_step));
     // the reference's own (sequential, input-dtype) mean replaces the f64 one when asked for
     const bool sequential = finalize == 1 && (mean_mode == PCR_MEAN_SEQUENTIAL || (mean_mode == PCR_MEAN_AUTO && n <= PCR_MEAN_AUTO_MAX_POINTS));
     if (sequential) {
@@ -332,6 +338,7 @@ int launch_transform(pcr_ctx* ctx, const void* d_in, int in_is_f64, long long n,
 // Type-erased raw source of the fused path (pcr_render_frames): K1 is evaluated inside K2a / K4.
 struct RawSrc {
     const void* in; int is_f64; long long frame_stride; int cols; const double* stats; const float* radius; const float* rgb;
+    const void* sample = nullptr; long long sample_stride = 0;    // every occlusion_step-th point (x, y, z), compact: K0 -> pre-pass
 };
 
 template <typename T>
@@ -415,14 +422,19 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
             const size_t sm2 = (size_t)tiles * 4 + (size_t)((hz_w1 + 3) / 4) * ((hz_h1 + 3) / 4) * 4 + (size_t)(BIN_THREADS / 32) * 5 * RING_CAP * 4;
             const int two_phase = (ctx->two_phase && hz && use_smem && !do_trails && sm2 <= (size_t)ctx->smem_optin / 2) ? 1 : 0;
             const size_t sm = two_phase ? sm2 : (use_smem ? (size_t)tiles * 4 : 0);
+            // the pre-pass reads the compact sample K0 wrote (point i of the pass = sample row i) when there is one
+            RawSrc rsrc = raw ? *raw : RawSrc{};
+            int fetch_step = step;
+            if (raw && step > 1 && raw->sample) { rsrc.in = raw->sample; rsrc.frame_stride = raw->sample_stride; rsrc.cols = 3; fetch_step = 1; }
+            const RawSrc* rawp = raw ? &rsrc : nullptr;
 #define PCR_PROJECT(T, RAWB, TRB, posarg, strarg, rawarg)                                                                        \
     LAUNCH(KID_PROJECT, stream, (k_project_count<T, RAWB, TRB><<<grid, BIN_THREADS, sm, stream>>>(                               \
-        posarg, np, strarg, rawarg, st, step, ctx->d_frames, ctx->sph, ctx->rect, ctx->ext, slots, bin, use_smem, hz, ctx->hz_cap, two_phase)))
+        posarg, np, strarg, rawarg, st, fetch_step, ctx->d_frames, ctx->sph, ctx->rect, ctx->ext, slots, bin, use_smem, hz, ctx->hz_cap, two_phase, step)))
             if (!raw) PCR_PROJECT(float, false, false, pos, in_stride, raw_frames<float>(nullptr));
-            else if (raw->is_f64 && do_trails) PCR_PROJECT(double, true, true, nullptr, 0, raw_frames<double>(raw));
-            else if (raw->is_f64) PCR_PROJECT(double, true, false, nullptr, 0, raw_frames<double>(raw));
-            else if (do_trails) PCR_PROJECT(float, true, true, nullptr, 0, raw_frames<float>(raw));
-            else PCR_PROJECT(float, true, false, nullptr, 0, raw_frames<float>(raw));
+            else if (raw->is_f64 && do_trails) PCR_PROJECT(double, true, true, nullptr, 0, raw_frames<double>(rawp));
+            else if (raw->is_f64) PCR_PROJECT(double, true, false, nullptr, 0, raw_frames<double>(rawp));
+            else if (do_trails) PCR_PROJECT(float, true, true, nullptr, 0, raw_frames<float>(rawp));
+            else PCR_PROJECT(float, true, false, nullptr, 0, raw_frames<float>(rawp));
 #undef PCR_PROJECT
         }
         LAUNCH(KID_SCAN, stream, k_scan_tiles<<<nb, 1024, 0, stream>>>(ctx->d_frames, bin, np, lazy ? (seeded ? 2 : 1) : 0));
@@ -551,6 +563,7 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     if (const char* e = getenv("PCR_OCCLUSION")) ctx->occlusion = atoi(e);
     if (const char* e = getenv("PCR_TWO_PHASE")) ctx->two_phase = atoi(e);
     if (const char* e = getenv("PCR_LAZY_FILL")) ctx->lazy_fill = atoi(e);
+    if (const char* e = getenv("PCR_SAMPLE_PREPASS")) ctx->sample_prepass = atoi(e);
     if (const char* e = getenv("PCR_SCATTER_THREADS")) ctx->scatter_threads = std::min(BIN_THREADS, std::max(32, atoi(e) & ~31));
     if (const char* e = getenv("PCR_OCCLUSION_STEP")) ctx->occlusion_step = std::max(2, atoi(e));
     const size_t B = (size_t)max_batch, N = (size_t)max_points, Tn = (size_t)ctx->tiles_cap;
@@ -619,7 +632,7 @@ void pcr_destroy(pcr_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     void* frees[] = {ctx->surv_count, ctx->ext, ctx->sph, ctx->rect, ctx->partials, ctx->stats, ctx->done, ctx->counts, ctx->offsets,
-                     ctx->cursor, ctx->p_sph, ctx->p_ci, ctx->p_ext, ctx->tile_state, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
+                     ctx->cursor, ctx->p_sph, ctx->p_ci, ctx->p_ext, ctx->tile_state, ctx->sample, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
                      ctx->stage_rgba[0], ctx->stage_rgba[1], ctx->stage_vis[0], ctx->stage_vis[1], ctx->stage_radius, ctx->stage_rgb,
                      ctx->peer_merged, ctx->peer_image, ctx->mesh_verts, ctx->mesh_prof, ctx->plan, ctx->dstats, ctx->dxf, ctx->dctrl, ctx->dcount};
     for (void* p : frees) if (p) cudaFree(p);
@@ -842,11 +855,27 @@ int pcr_render_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, 
             CK(cudaEventCreateWithFlags(&ctx->ev_free[k], cudaEventDisableTiming));
         }
     }
+    // occluder pre-pass ahead (same condition as launch_render): K0 also writes the compact sample it will read
+    const bool occl = ctx->occlusion > 0 || (ctx->occlusion < 0 && n >= ctx->occlusion_min_points);
+    const int sstep = ctx->occlusion_step;
+    const bool sampled = ctx->sample_prepass && occl && n > sstep;
+    const long long sample_stride = sampled ? ((n + sstep - 1) / sstep) * 3 : 0;          // elements per frame
+    if (sampled) {
+        const size_t need = 2 * (size_t)B * (size_t)sample_stride * elem;
+        if (ctx->sample_bytes < need) {
+            CK(cudaDeviceSynchronize());
+            if (ctx->sample) CK(cudaFree(ctx->sample));
+            ctx->sample = nullptr; ctx->sample_bytes = 0;
+            CK(cudaMalloc(&ctx->sample, need));
+            ctx->sample_bytes = need;
+        }
+    }
+    auto sample_of = [&](int k) -> char* { return sampled ? (char*)ctx->sample + (size_t)(k & 1) * B * (size_t)sample_stride * elem : nullptr; };
     auto stats_of = [&](int k, cudaStream_t q) -> int {
         const int f0 = k * B, nb = std::min(B, n_frames - f0);
         const char* in = (const char*)d_in + (size_t)f0 * frame_stride * elem;
         return launch_stats(ctx, in, in_is_f64, n, cols, frame_stride, nb, ctx->partials, ctx->stats + (size_t)(k & 1) * B * 10, 1, q,
-                            style->mean_mode);
+                            style->mean_mode, sample_of(k), sample_stride, sstep);
     };
     if (ahead) {
         CK(cudaEventRecord(ctx->ev_fork, s));                       // the input may still be in flight on the caller's stream
@@ -875,7 +904,8 @@ int pcr_render_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, 
             if (rc) return rc;
         }
         // no K1 launch: K2a and K4 evaluate standardise/transform/colour from the raw frames on the fly
-        const RawSrc raw = {in, in_is_f64, frame_stride, cols, stats, d_radius, d_rgb};
+        RawSrc raw = {in, in_is_f64, frame_stride, cols, stats, d_radius, d_rgb};
+        raw.sample = sample_of(k); raw.sample_stride = sample_stride;
         uint64_t* vis = d_vis ? d_vis + (size_t)f0 * px : ctx->vis;
         const long long vis_stride = d_vis ? px : (long long)ctx->max_w * ctx->max_h;
         rc = launch_render(ctx, nullptr, nullptr, 0, &raw, n, nb, 0u, st, W, H, vis, vis_stride,
