@@ -593,3 +593,36 @@ def test_hoisted_scale_division_is_ieee_exact(ctx):
     divisors += [1.0, 2.0, 0.5, 3.0, 1.9999999, 1.0000001, 0.99999994, 7.9999995, 2.0 ** -40, 2.0 ** 40, 2.0 ** -41, 2.0 ** 41,
                  1e-30, 1e30, 1.1754944e-38, 3.4028235e38]
     assert ctx.selftest_scale_div(divisors) == 0
+
+
+@pytest.mark.parametrize("switch", ["PCR_LAZY_FILL", "PCR_SAMPLE_PREPASS", "PCR_TWO_PHASE"])
+def test_work_saving_devices_never_change_a_result(lib, orc, switch, monkeypatch):
+    """Lazy floor fill, the compact pre-pass sample written by K0 and the two-phase cull of K2a only move or skip work:
+    with each of them switched off (environment switch read by pcr_create) the fused whole-path entry returns the same
+    keys and the same image, on a dense cloud with the occlusion pre-pass and on a small one without; the dense
+    frame's keys are also checked against the oracle."""
+    cfg = PRESETS["traj_ball"].for_trajectory(100)
+    outs = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv(switch, "0")
+        c = _native.Context(device=0, max_points=300_000, max_w=800, max_h=608, max_batch=2)
+        try:
+            res = []
+            for n, W, H in ((300_000, 800, 608), (5_000, 640, 360)):
+                traj = synthetic.trajectory(3, n, 3, seed=11)
+                cams = [cfg.camera(97 + f, 100, W, H) for f in range(3)]
+                rgba, vis = c.render_frames(dev(traj), cams, cfg.style(), want_vis=True)
+                res.append((rgba.cpu().numpy(), keys(vis)))
+            outs.append(res)
+        finally:
+            c.close()
+    for (rgba_on, vis_on), (rgba_off, vis_off) in zip(*outs):
+        np.testing.assert_array_equal(vis_on, vis_off)
+        np.testing.assert_array_equal(rgba_on, rgba_off)
+    # the dense case against the oracle (f64 mean above 131072 points)
+    traj = synthetic.trajectory(3, 300_000, 3, seed=11)
+    p = orc.transform_coordinates(orc.standardize_point_cloud(traj[2], exact_mean=True), cfg.flip_x)
+    pos4 = np.concatenate([p, np.full((len(p), 1), cfg.radius, np.float32)], axis=1)
+    want = orc.visibility(pos4, orc_frame(orc, cfg, 99, 100, 800, 608), orc_scene(orc, cfg))
+    np.testing.assert_array_equal(outs[0][0][1][2], want)
