@@ -64,6 +64,7 @@ struct pcr_ctx {
     void* sample = nullptr;           // [2][max_batch][ceil(n/step)][3] every step-th point of a frame, written by K0 for the pre-pass
     size_t sample_bytes = 0;
     int sample_prepass = 1;           // PCR_SAMPLE_PREPASS=0 disables (diagnostics)
+    int stats_ahead = 1;              // K0 of batch k+1 on a second stream while batch k renders (PCR_STATS_AHEAD=0: in line)
     float4* p_ext = nullptr;          // capsule end B — allocated when the first frames with trails arrive
     int raster_ctas_per_sm[2] = {4, 2};   // k_raster_tiles<false / true>: resident CTAs per SM (occupancy query)
     unsigned long long* stat_pairs = nullptr;
@@ -564,6 +565,7 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     if (const char* e = getenv("PCR_TWO_PHASE")) ctx->two_phase = atoi(e);
     if (const char* e = getenv("PCR_LAZY_FILL")) ctx->lazy_fill = atoi(e);
     if (const char* e = getenv("PCR_SAMPLE_PREPASS")) ctx->sample_prepass = atoi(e);
+    if (const char* e = getenv("PCR_STATS_AHEAD")) ctx->stats_ahead = atoi(e);
     if (const char* e = getenv("PCR_SCATTER_THREADS")) ctx->scatter_threads = std::min(BIN_THREADS, std::max(32, atoi(e) & ~31));
     if (const char* e = getenv("PCR_OCCLUSION_STEP")) ctx->occlusion_step = std::max(2, atoi(e));
     const size_t B = (size_t)max_batch, N = (size_t)max_points, Tn = (size_t)ctx->tiles_cap;
@@ -844,7 +846,7 @@ int pcr_render_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, 
     // K0 (and the serial reference-exact mean, when selected) of batch k+1 runs on a second stream
     // while batch k renders; the stats array is double-buffered.  The serial mean is pure latency
     // (one warp per frame), so it hides completely behind a full batch of render kernels.
-    const bool ahead = nbatches > 1;
+    const bool ahead = nbatches > 1 && ctx->stats_ahead != 0;
     if (ahead && !ctx->s_aux) {
         int lo = 0, hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
