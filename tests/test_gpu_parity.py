@@ -626,3 +626,23 @@ def test_work_saving_devices_never_change_a_result(lib, orc, switch, monkeypatch
     pos4 = np.concatenate([p, np.full((len(p), 1), cfg.radius, np.float32)], axis=1)
     want = orc.visibility(pos4, orc_frame(orc, cfg, 99, 100, 800, 608), orc_scene(orc, cfg))
     np.testing.assert_array_equal(outs[0][0][1][2], want)
+
+
+@pytest.mark.parametrize("n", [511, 512, 513, 4095, 4096, 4097, 9001])
+def test_raster_item_and_chunk_boundaries(ctx, orc, n):
+    """K3 streams a work item (one tile, at most 4096 pairs) through its shared-memory ring in chunks of 512 pairs
+    with 16-byte-granular bulk copies; a tile with more pairs is split into several items that merge with atomicMin.
+    n tiny spheres whose pixel boxes all lie inside ONE 16x16 tile put exactly n pairs into that tile: the counts
+    straddle every boundary (last chunk of 1 or 511 pairs, exactly one full item, one item + 1 pair, three items).
+    The film is sized so that the look-at target projects onto the centre of a tile."""
+    cfg = PRESETS["traj_ball"]
+    W, H = 1008, 624                                   # centre pixel (504, 312): both = 8 mod 16
+    rng = np.random.default_rng(n)
+    target = np.array(cfg.target, np.float32)
+    pos = target[None, :] + rng.uniform(-0.002, 0.002, (n, 3)).astype(np.float32)
+    pos4 = np.concatenate([pos, np.full((n, 1), 0.004, np.float32)], axis=1)
+    got = render_case(ctx, orc, pos4, cfg, 199, 220, W, H)
+    ids = (got & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    hit = np.argwhere(ids < n)
+    assert len(hit) > 10
+    assert hit[:, 0].min() // 16 == hit[:, 0].max() // 16 and hit[:, 1].min() // 16 == hit[:, 1].max() // 16     # one tile
