@@ -646,3 +646,26 @@ def test_raster_item_and_chunk_boundaries(ctx, orc, n):
     hit = np.argwhere(ids < n)
     assert len(hit) > 10
     assert hit[:, 0].min() // 16 == hit[:, 0].max() // 16 and hit[:, 1].min() // 16 == hit[:, 1].max() // 16     # one tile
+
+
+def test_visibility_buffer_on_an_8_byte_boundary(lib, orc):
+    """The raster prefetches a tile's current keys with 16-byte-granular bulk copies; a caller's visibility buffer
+    that is only 8-byte aligned must fall back to plain loads (dense cloud with the pre-pass on, so that the seeded
+    main pass and split tiles are exercised)."""
+    n, W, H = 200_000, 640, 480
+    cfg = PRESETS["traj_ball"]
+    p = orc.transform_coordinates(orc.standardize_point_cloud(synthetic.cloud(n, "gauss", 5)), True)
+    pos4 = dev(np.concatenate([p, np.full((n, 1), 0.01, np.float32)], axis=1))
+    attr4 = dev(np.full((n, 4), 0.3, np.float32))
+    cam, style = cfg.camera(150, 220, W, H), cfg.style()
+    c = _native.Context(device=0, max_points=n, max_w=W, max_h=H, max_batch=1)
+    try:
+        c.set_occlusion(mode=1, step=8)
+        vis_a, rgba_a = c.render(pos4, attr4, cam, style)
+        backing = torch.empty(W * H + 1, dtype=torch.int64, device="cuda")
+        odd = backing[1:].view(H, W)
+        assert odd.data_ptr() % 16 == 8
+        vis_b, rgba_b = c.render(pos4, attr4, cam, style, out_vis=odd)
+        assert torch.equal(vis_a, vis_b) and torch.equal(rgba_a, rgba_b)
+    finally:
+        c.close()
