@@ -62,6 +62,7 @@ struct pcr_ctx {
     unsigned int* tile_state = nullptr;   // [max_batch][tiles_cap] lazy floor fill (BinDev::tile_state)
     unsigned long long* scan_part = nullptr;    // k_scan_tiles: per-stripe totals / ready flags (BinDev)
     unsigned int* scan_ready = nullptr;
+    unsigned int *fill_list = nullptr, *fill_count = nullptr;    // lazy floor fill: tiles k_fill_tiles has to visit (BinDev)
     int scan_stripes = 1;
     unsigned int scan_epoch = 0;
     int lazy_fill = 1;                // PCR_LAZY_FILL=0 disables (diagnostics)
@@ -253,6 +254,7 @@ BinDev bin_of(pcr_ctx* c)
     b.counts = c->counts; b.offsets = c->offsets; b.cursor = c->cursor;
     b.p_sph = c->p_sph; b.p_ci = c->p_ci; b.p_ext = c->p_ext; b.tile_state = nullptr;
     b.scan_part = c->scan_part; b.scan_ready = c->scan_ready; b.scan_stripes = c->scan_stripes;
+    b.fill_list = c->fill_list; b.fill_count = c->fill_count;
     b.overflow = c->overflow; b.stat_pairs = c->stat_pairs; b.tiles_cap = c->tiles_cap; b.pair_cap = c->pair_cap;
     b.item_count = c->item_count; b.item_next = c->item_next; b.items = c->items; b.item_cap = c->item_cap;
     b.surv_count = c->surv_count; b.gx_cap = c->gx_cap;
@@ -445,10 +447,11 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
 #undef PCR_PROJECT
         }
         if (++ctx->scan_epoch == 0u) ctx->scan_epoch = 1u;            // 0 = the flags' initial value
-        LAUNCH(KID_SCAN, stream, k_scan_tiles<<<dim3((unsigned)((tiles + 4095) / 4096), nb), 1024, 0, stream>>>(ctx->d_frames, bin, np, lazy ? (seeded ? 2 : 1) : 0, ctx->scan_epoch));
+        LAUNCH(KID_SCAN, stream, k_scan_tiles<<<dim3((unsigned)((tiles + 4095) / 4096), nb), 1024, 0, stream>>>(ctx->d_frames, bin, np, lazy ? (seeded ? 2 : 1) : 0, ctx->scan_epoch,
+                                                                                                                    lazy ? hz_out : nullptr, ctx->hz_cap));
         if (lazy && seeded) {
             // tiles only the main pass touches need the floor keys the raster starts from
-            dim3 grid((unsigned)std::max(1, std::min((tiles + 7) / 8, ctx->num_sms * 32 / nb)), nb);
+            dim3 grid((unsigned)std::max(1, std::min(std::min((tiles + 7) / 8, ctx->num_sms * 32 / nb), 16)), nb);   // a short list per frame
             LAUNCH(KID_FILL, stream, k_fill_tiles<<<grid, 256, 0, stream>>>(ctx->d_frames, st, bin, v, vis_stride, nullptr, ctx->hz_cap, 2));
         }
         if (np > 0) {
@@ -464,7 +467,7 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         }
         if (!seeded) {
             // floor keys of empty tiles, all-ones preset of split tiles
-            dim3 grid((unsigned)std::max(1, std::min((tiles + 7) / 8, ctx->num_sms * 32 / nb)), nb);
+            dim3 grid((unsigned)std::max(1, std::min(std::min((tiles + 7) / 8, ctx->num_sms * 32 / nb), lazy ? 16 : 1 << 30)), nb);
             LAUNCH(KID_FILL, stream, k_fill_tiles<<<grid, 256, 0, stream>>>(ctx->d_frames, st, bin, v, vis_stride, hz_out, ctx->hz_cap, lazy ? 1 : 0));
         }
         if (np > 0) {
@@ -608,7 +611,9 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     ALLOC(ctx->offsets, sizeof(unsigned int) * B * (Tn + 4));   // per-frame stride tiles_cap + 4 keeps uint4 alignment
     ALLOC(ctx->cursor, sizeof(unsigned int) * B * Tn);
     ctx->scan_stripes = (int)((Tn + 4095) / 4096);
-    ALLOC(ctx->scan_part, sizeof(unsigned long long) * B * (size_t)ctx->scan_stripes * 2);
+    ALLOC(ctx->scan_part, sizeof(unsigned long long) * B * (size_t)ctx->scan_stripes * 3);
+    ALLOC(ctx->fill_list, sizeof(unsigned int) * B * Tn);
+    ALLOC(ctx->fill_count, sizeof(unsigned int) * B);
     ALLOC(ctx->scan_ready, sizeof(unsigned int) * B * (size_t)ctx->scan_stripes);
     ALLOC(ctx->tile_state, sizeof(unsigned int) * (2 * B * Tn + B));     // [state | active list | active count]
     ALLOC(ctx->p_sph, sizeof(float4) * B * (size_t)ctx->pair_cap);
@@ -645,7 +650,7 @@ void pcr_destroy(pcr_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     void* frees[] = {ctx->surv_count, ctx->ext, ctx->sph, ctx->rect, ctx->partials, ctx->stats, ctx->done, ctx->counts, ctx->offsets,
-                     ctx->cursor, ctx->p_sph, ctx->p_ci, ctx->p_ext, ctx->tile_state, ctx->sample, ctx->scan_part, ctx->scan_ready, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
+                     ctx->cursor, ctx->p_sph, ctx->p_ci, ctx->p_ext, ctx->tile_state, ctx->sample, ctx->scan_part, ctx->scan_ready, ctx->fill_list, ctx->fill_count, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
                      ctx->stage_rgba[0], ctx->stage_rgba[1], ctx->stage_vis[0], ctx->stage_vis[1], ctx->stage_radius, ctx->stage_rgb,
                      ctx->peer_merged, ctx->peer_image, ctx->mesh_verts, ctx->mesh_prof, ctx->plan, ctx->dstats, ctx->dxf, ctx->dctrl, ctx->dcount};
     for (void* p : frees) if (p) cudaFree(p);
