@@ -491,8 +491,8 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         int rc = pass((n + step - 1) / step, step, nullptr, 0, 0, no_peer, ctx->hz);       // trails are never occluders; only the final pass pushes
         if (rc) return rc;
         // level-1 Hi-Z entries were written by k_fill_tiles (empty tiles) and the raster (single-item tiles)
-        dim3 grid((unsigned)((tiles + 7) / 8), nb);
-        LAUNCH(KID_HIZ, stream, k_hiz_split<<<grid, 256, 0, stream>>>(ctx->d_frames, bin, v, vis_stride, ctx->hz, ctx->hz_cap));
+        dim3 grid((unsigned)(lazy ? std::min((tiles + 7) / 8, 8) : (tiles + 7) / 8), nb);
+        LAUNCH(KID_HIZ, stream, k_hiz_split<<<grid, 256, 0, stream>>>(ctx->d_frames, bin, v, vis_stride, ctx->hz, ctx->hz_cap, lazy ? 1 : 0));
         const int hzn2 = (((W + HZ_W - 1) / HZ_W + 3) / 4) * (((H + HZ_H - 1) / HZ_H + 3) / 4);
         dim3 grid2((unsigned)((hzn2 + 255) / 256), nb);
         LAUNCH(KID_HIZ, stream, k_hiz2<<<grid2, 256, 0, stream>>>(ctx->d_frames, ctx->hz, ctx->hz_cap));
