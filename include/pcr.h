@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PCR_ABI_VERSION 3
+#define PCR_ABI_VERSION 4
 
 /* Point ids stored in the low 32 bits of a visibility key. */
 #define PCR_ID_FLOOR 0xFFFFFFFEu
@@ -193,6 +193,15 @@ int pcr_velocity_trails(pcr_ctx* ctx, const float* d_pcl6, int64_t n, const pcr_
 int pcr_render(pcr_ctx* ctx, const float* d_pos, const float* d_attr, int64_t n,
                uint32_t id_base, const pcr_camera* cam, const pcr_style* style,
                uint64_t* d_vis, uint8_t* d_rgba, void* stream);
+
+/* render_scene for a frame that is ALREADY standardised and transformed — the (n, 3|6) float32 array process() hands to
+ * generate_xml_content (traj_ball_renderer.py:309-333, example_renderer.py:113-128): one sphere per row and, for 6
+ * columns with style->trails == 1, the velocity trail _add_velocity_trail draws for every point (id n + index,
+ * length scale cam->trail_scale).  Positions / velocities are used bit for bit as given (style->xform and mean_mode are
+ * ignored).  d_vis may be NULL.  This is what the facade's process() calls, so a reference-named entry point draws what
+ * the reference draws. */
+int pcr_render_transformed(pcr_ctx* ctx, const float* d_pcl, int64_t n, int cols, const float* d_radius, const float* d_rgb,
+                           const pcr_camera* cam, const pcr_style* style, uint64_t* d_vis, uint8_t* d_rgba, void* stream);
 
 /* K4 alone — shade a (possibly merged) visibility buffer.  Points whose id is outside
  * [id_base, id_base+n) are shaded only when owner_only == 0 is impossible for them, so:

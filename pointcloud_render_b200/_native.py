@@ -27,7 +27,7 @@ SYMBOLS = (
     "pcr_transform_coordinates", "pcr_profile", "pcr_profile_read", "pcr_kernel_name", "pcr_set_occlusion", "pcr_finalize_stats", "pcr_velocity_trails", "pcr_render_shard", "pcr_shade_shard",
     "pcr_set_droplet_mesh", "pcr_droplet_transforms", "pcr_history_trails", "pcr_render_droplet_frames",
     "pcr_peer_alloc", "pcr_ipc_export", "pcr_ipc_open", "pcr_ipc_close", "pcr_peer_set", "pcr_peer_begin_frame",
-    "pcr_render_shard_peer", "pcr_shade_shard_peer", "pcr_selftest_scale_div",
+    "pcr_render_shard_peer", "pcr_shade_shard_peer", "pcr_selftest_scale_div", "pcr_render_transformed",
 )
 HISTORY_FRAMES, MAX_CTRL = 20, 21                   # PCR_HISTORY_FRAMES, PCR_MAX_CTRL
 TRAILS_NONE, TRAILS_VELOCITY, TRAILS_HISTORY = 0, 1, 2
@@ -84,6 +84,7 @@ def load_library():
     L.pcr_standardize.argtypes = [vp, vp, i32, i64, i32, vp, vp, styp, vp, vp, vp, vp, vp]
     L.pcr_render.argtypes = [vp, vp, vp, i64, u32, camp, styp, vp, vp, vp]
     L.pcr_shade.argtypes = [vp, vp, vp, vp, i64, u32, i32, camp, styp, vp, vp]
+    L.pcr_render_transformed.argtypes = [vp, vp, i64, i32, vp, vp, camp, styp, vp, vp, vp]
     L.pcr_render_frames.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, camp, styp, vp, vp, vp]
     L.pcr_render_frames_host.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, camp, styp, vp, vp]
     L.pcr_zmin.argtypes = [vp, vp, vp, i64, vp]
@@ -165,6 +166,38 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+def _check_points(t, cuda=True, dims=2, f32_only=False, what="points"):
+    """Every wrapper hands raw pointers to C: a wrong dtype, a strided view (cloud[:, :3] of an (N,6) tensor) or
+    a tensor on the wrong device would be silently reinterpreted / read out of bounds.  Raises instead."""
+    import torch
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{what}: expected a torch tensor, got {type(t).__name__}")
+    ok = (torch.float32,) if f32_only else (torch.float32, torch.float64)
+    if t.dtype not in ok:
+        raise TypeError(f"{what}: dtype must be {' or '.join(str(d) for d in ok)}, got {t.dtype}")
+    if t.is_cuda != bool(cuda):
+        raise ValueError(f"{what}: must be a {'CUDA' if cuda else 'CPU'} tensor")
+    if t.dim() != dims or t.shape[-1] not in (3, 6):
+        raise ValueError(f"{what}: shape must be {'(F,N,3|6)' if dims == 3 else '(N,3|6)'}, got {tuple(t.shape)}")
+    if not t.is_contiguous():
+        raise ValueError(f"{what}: must be contiguous (got strides {t.stride()}); call .contiguous()")
+    return t
+
+
+def _check_vector(t, numel, cuda=True, dtype=None, what="array"):
+    """Optional per-point arrays (radius [n], rgb [n][3], stats [10] ...): dtype, size, device, contiguity."""
+    import torch
+    if t is None:
+        return None
+    dtype = dtype or torch.float32
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{what}: expected a torch tensor, got {type(t).__name__}")
+    if t.dtype != dtype or t.numel() != int(numel) or t.is_cuda != bool(cuda) or not t.is_contiguous():
+        raise ValueError(f"{what}: expected a contiguous {'CUDA' if cuda else 'CPU'} {dtype} tensor of {int(numel)} elements, "
+                         f"got {t.dtype} x {t.numel()} on {t.device}")
+    return t
+
+
 def _stream_ptr(stream):
     import torch
     s = stream if stream is not None else torch.cuda.current_stream()
@@ -208,10 +241,10 @@ class Context:
     def standardize(self, pts, style, radius=None, rgb=None, want_vel=False, want_stats=False, stream=None):
         """pts: (N,3|6) float32/float64 CUDA tensor -> pos4 (N,4), attr4 (N,4)[, vel4][, stats(10)]."""
         import torch
-        assert pts.is_cuda and pts.is_contiguous() and pts.dim() == 2
+        _check_points(pts)
         n, cols = pts.shape
         is64 = pts.dtype == torch.float64
-        assert is64 or pts.dtype == torch.float32
+        _check_vector(radius, n, what="radius"); _check_vector(rgb, 3 * n, what="rgb")
         dev = pts.device
         pos = torch.empty((n, 4), dtype=torch.float32, device=dev)
         attr = torch.empty((n, 4), dtype=torch.float32, device=dev)
@@ -230,7 +263,7 @@ class Context:
     def transform_coordinates(self, pcl, flip_x=True, z_lift=0.0125, stream=None):
         """(N,3|6) float32 CUDA tensor -> transformed copy (transform_coordinates alone)."""
         import torch
-        assert pcl.is_cuda and pcl.is_contiguous() and pcl.dtype == torch.float32
+        _check_points(pcl, f32_only=True)
         n, cols = pcl.shape
         out = torch.empty_like(pcl)
         self._check(self.lib.pcr_transform_coordinates(self.handle, _ptr(pcl), n, cols, int(bool(flip_x)), float(z_lift),
@@ -240,7 +273,9 @@ class Context:
     def velocity_trails(self, pcl6, style, trail_scale, stream=None):
         """(N,6) float32 CUDA tensor (transformed) -> tail (N,3), head (N,3) float32, valid (N,) uint8."""
         import torch
-        assert pcl6.is_cuda and pcl6.is_contiguous() and pcl6.dtype == torch.float32 and pcl6.shape[1] == 6
+        _check_points(pcl6, f32_only=True)
+        if pcl6.shape[1] != 6:
+            raise ValueError("velocity_trails needs (N,6) points")
         n = pcl6.shape[0]
         tail = torch.empty((n, 3), dtype=torch.float32, device=pcl6.device)
         head = torch.empty((n, 3), dtype=torch.float32, device=pcl6.device)
@@ -251,6 +286,7 @@ class Context:
 
     def stats_partial(self, pts, stream=None):
         import torch
+        _check_points(pts)
         n, cols = pts.shape
         out = torch.empty(10, dtype=torch.float64, device=pts.device)
         self._check(self.lib.pcr_stats_partial(self.handle, _ptr(pts), int(pts.dtype == torch.float64), n, cols,
@@ -269,7 +305,10 @@ class Context:
     def standardize_with_stats(self, pts, style, stats10, radius=None, rgb=None, stream=None, out=None):
         """out = (pos4, attr4) reuses caller buffers (no allocation per call)."""
         import torch
+        _check_points(pts)
         n, cols = pts.shape
+        _check_vector(stats10, 10, dtype=torch.float64, what="stats10")
+        _check_vector(radius, n, what="radius"); _check_vector(rgb, 3 * n, what="rgb")
         pos = out[0] if out is not None else torch.empty((n, 4), dtype=torch.float32, device=pts.device)
         attr = out[1] if out is not None else torch.empty((n, 4), dtype=torch.float32, device=pts.device)
         self._check(self.lib.pcr_standardize_with_stats(self.handle, _ptr(pts), int(pts.dtype == torch.float64), n, cols,
@@ -282,6 +321,7 @@ class Context:
         """pos4/attr4: (N,4) float32 CUDA -> vis (H,W) int64 view of the uint64 keys, rgba (H,W,4) uint8."""
         import torch
         n = pos4.shape[0]
+        _check_vector(pos4, 4 * n, what="pos4"); _check_vector(attr4, 4 * n, what="attr4")
         dev = pos4.device
         vis = out_vis if out_vis is not None else torch.empty((cam.height, cam.width), dtype=torch.int64, device=dev)
         rgba = (out_rgba if out_rgba is not None else torch.empty((cam.height, cam.width, 4), dtype=torch.uint8, device=dev)) if shade else None
@@ -289,10 +329,25 @@ class Context:
                                         ctypes.byref(cam), ctypes.byref(style), _ptr(vis), _ptr(rgba), _stream_ptr(stream)))
         return vis, rgba
 
+    def render_transformed(self, pcl, cam, style, radius=None, rgb=None, want_vis=True, stream=None):
+        """pcl: (N,3|6) float32 CUDA tensor, already standardised + transformed (what generate_xml_content gets) ->
+        vis (H,W) int64, rgba (H,W,4) uint8.  6 columns + style.trails: spheres AND their velocity trails."""
+        import torch
+        _check_points(pcl, f32_only=True)
+        n, cols = pcl.shape
+        _check_vector(radius, n, what="radius"); _check_vector(rgb, 3 * n, what="rgb")
+        vis = torch.empty((cam.height, cam.width), dtype=torch.int64, device=pcl.device) if want_vis else None
+        rgba = torch.empty((cam.height, cam.width, 4), dtype=torch.uint8, device=pcl.device)
+        self._check(self.lib.pcr_render_transformed(self.handle, _ptr(pcl) if n else None, n, cols, _ptr(radius), _ptr(rgb),
+                                                    ctypes.byref(cam), ctypes.byref(style), _ptr(vis), _ptr(rgba), _stream_ptr(stream)))
+        return vis, rgba
+
     def shade(self, vis, pos4, attr4, cam, style, id_base=0, owner_only=False, stream=None, out_rgba=None):
         import torch
         rgba = out_rgba if out_rgba is not None else torch.empty((cam.height, cam.width, 4), dtype=torch.uint8, device=vis.device)
         n = pos4.shape[0]
+        _check_vector(pos4, 4 * n, what="pos4"); _check_vector(attr4, 4 * n, what="attr4")
+        _check_vector(vis, cam.height * cam.width, dtype=torch.int64, what="vis")
         self._check(self.lib.pcr_shade(self.handle, _ptr(vis), _ptr(pos4) if n else None, _ptr(attr4) if n else None, n,
                                        int(id_base), int(owner_only), ctypes.byref(cam), ctypes.byref(style), _ptr(rgba),
                                        _stream_ptr(stream)))
@@ -301,7 +356,10 @@ class Context:
     def render_shard(self, pts, stats10, cam, style, id_base=0, radius=None, rgb=None, out_vis=None, stream=None):
         """One shard of a point-sharded cloud, fused path: raw (n, 3|6) points + global stats -> vis keys."""
         import torch
+        _check_points(pts)
         n, cols = pts.shape
+        _check_vector(stats10, 10, dtype=torch.float64, what="stats10")
+        _check_vector(radius, n, what="radius"); _check_vector(rgb, 3 * n, what="rgb")
         vis = out_vis if out_vis is not None else torch.empty((cam.height, cam.width), dtype=torch.int64, device=pts.device)
         self._check(self.lib.pcr_render_shard(self.handle, _ptr(pts) if n else None, int(pts.dtype == torch.float64), n, cols, _ptr(radius),
                                               _ptr(rgb), _ptr(stats10), int(id_base), ctypes.byref(cam), ctypes.byref(style), _ptr(vis),
@@ -310,7 +368,11 @@ class Context:
 
     def shade_shard(self, vis, pts, stats10, cam, style, id_base=0, owner_only=True, radius=None, rgb=None, out_rgba=None, stream=None):
         import torch
+        _check_points(pts)
         n, cols = pts.shape
+        _check_vector(stats10, 10, dtype=torch.float64, what="stats10")
+        _check_vector(vis, cam.height * cam.width, dtype=torch.int64, what="vis")
+        _check_vector(radius, n, what="radius"); _check_vector(rgb, 3 * n, what="rgb")
         rgba = out_rgba if out_rgba is not None else torch.empty((cam.height, cam.width, 4), dtype=torch.uint8, device=vis.device)
         self._check(self.lib.pcr_shade_shard(self.handle, _ptr(vis), _ptr(pts) if n else None, int(pts.dtype == torch.float64), n, cols,
                                              _ptr(radius), _ptr(rgb), _ptr(stats10), int(id_base), int(owner_only), ctypes.byref(cam),
@@ -321,9 +383,11 @@ class Context:
                       stream=None):
         """traj: (F,N,3|6) CUDA tensor; cams: list of Camera -> rgba (F,H,W,4) uint8 [, vis (F,H,W) int64]."""
         import torch
-        assert traj.is_cuda and traj.is_contiguous() and traj.dim() == 3
+        _check_points(traj, dims=3, what="traj")
         F, n, cols = traj.shape
-        assert len(cams) == F
+        if len(cams) != F:
+            raise ValueError("one camera per frame")
+        _check_vector(radius, n, what="radius"); _check_vector(rgb, 3 * n, what="rgb")
         if F == 0:
             return (torch.empty((0, 0, 0, 4), dtype=torch.uint8, device=traj.device), None) if want_vis else \
                 torch.empty((0, 0, 0, 4), dtype=torch.uint8, device=traj.device)
@@ -341,9 +405,12 @@ class Context:
         """Host-buffer entry (what a reference script would call): traj_host is a CPU tensor or
         numpy array (F,N,3|6), ideally pinned; returns rgba as a CPU tensor (F,H,W,4).  Synchronous."""
         import torch
-        t = torch.as_tensor(traj_host)
-        assert not t.is_cuda and t.is_contiguous() and t.dim() == 3
+        t = _check_points(torch.as_tensor(traj_host), cuda=False, dims=3, what="traj_host")
         F, n, cols = t.shape
+        if len(cams) != F:
+            raise ValueError("one camera per frame")
+        radius_host = None if radius_host is None else _check_vector(torch.as_tensor(radius_host), n, cuda=False, what="radius_host")
+        rgb_host = None if rgb_host is None else _check_vector(torch.as_tensor(rgb_host), 3 * n, cuda=False, what="rgb_host")
         W, H = cams[0].width, cams[0].height
         cam_arr = (Camera * F)(*cams)
         rgba = out_rgba if out_rgba is not None else torch.empty((F, H, W, 4), dtype=torch.uint8).pin_memory()
@@ -364,8 +431,9 @@ class Context:
     def droplet_transforms(self, pcl, rot=None, stream=None):
         """(N,3|6) float32 CUDA tensor (transformed) [+ rot (N,9) for 3 columns] -> (N,12) rows [R | position]."""
         import torch
-        assert pcl.is_cuda and pcl.is_contiguous() and pcl.dtype == torch.float32
+        _check_points(pcl, f32_only=True)
         n, cols = pcl.shape
+        _check_vector(rot, 9 * n, what="rot")
         xf = torch.empty((n, 12), dtype=torch.float32, device=pcl.device)
         self._check(self.lib.pcr_droplet_transforms(self.handle, _ptr(pcl), n, cols, _ptr(rot), _ptr(xf), _stream_ptr(stream)))
         return xf
@@ -373,9 +441,10 @@ class Context:
     def history_trails(self, hist, pos, stream=None):
         """hist (h,N,3), pos (N,3) float32 CUDA tensors (transformed) -> ctrl (N,21,3) float32, count (N,) int32."""
         import torch
-        assert pos.is_cuda and pos.is_contiguous() and pos.dtype == torch.float32
-        assert hist.is_contiguous() and hist.dtype == torch.float32
+        _check_points(pos, f32_only=True, what="pos")
         n = pos.shape[0]
+        if hist.dim() != 3 or hist.shape[1:] != (n, 3) or hist.dtype != torch.float32 or not hist.is_contiguous() or (hist.shape[0] and not hist.is_cuda):
+            raise ValueError("hist: expected a contiguous float32 CUDA tensor (h, N, 3)")
         ctrl = torch.zeros((n, MAX_CTRL, 3), dtype=torch.float32, device=pos.device)
         count = torch.empty(n, dtype=torch.int32, device=pos.device)
         self._check(self.lib.pcr_history_trails(self.handle, _ptr(hist) if hist.shape[0] else None, int(hist.shape[0]), _ptr(pos), n,
@@ -386,10 +455,12 @@ class Context:
         """traj: (n_history + F, N, 3|6) CUDA tensor — the F frames to render preceded by their history halo;
         cams: F cameras -> rgba (F,H,W,4) uint8 [, vis (F,H,W) int64]."""
         import torch
-        assert traj.is_cuda and traj.is_contiguous() and traj.dim() == 3
+        _check_points(traj, dims=3, what="traj")
         total, n, cols = traj.shape
         F = total - int(n_history)
-        assert F >= 0 and len(cams) == F
+        if F < 0 or len(cams) != F:
+            raise ValueError("one camera per rendered frame (frames after the history halo)")
+        _check_vector(rot, 9 * n, what="rot")
         W, H = (cams[0].width, cams[0].height) if F else (0, 0)
         rgba = out_rgba if out_rgba is not None else torch.empty((F, H, W, 4), dtype=torch.uint8, device=traj.device)
         vis = out_vis if out_vis is not None else (torch.empty((F, H, W), dtype=torch.int64, device=traj.device) if want_vis else None)
@@ -432,7 +503,10 @@ class Context:
 
     def render_shard_peer(self, pts, stats10, cam, style, id_base=0, radius=None, rgb=None, out_vis=None, stream=None):
         import torch
+        _check_points(pts)
         n, cols = pts.shape
+        _check_vector(stats10, 10, dtype=torch.float64, what="stats10")
+        _check_vector(radius, n, what="radius"); _check_vector(rgb, 3 * n, what="rgb")
         vis = out_vis if out_vis is not None else torch.empty((cam.height, cam.width), dtype=torch.int64, device=pts.device)
         self._check(self.lib.pcr_render_shard_peer(self.handle, _ptr(pts) if n else None, int(pts.dtype == torch.float64), n, cols,
                                                    _ptr(radius), _ptr(rgb), _ptr(stats10), int(id_base), ctypes.byref(cam),
@@ -441,7 +515,10 @@ class Context:
 
     def shade_shard_peer(self, vis, pts, stats10, cam, style, id_base=0, radius=None, rgb=None, stream=None):
         import torch
+        _check_points(pts)
         n, cols = pts.shape
+        _check_vector(stats10, 10, dtype=torch.float64, what="stats10")
+        _check_vector(radius, n, what="radius"); _check_vector(rgb, 3 * n, what="rgb")
         self._check(self.lib.pcr_shade_shard_peer(self.handle, _ptr(vis), _ptr(pts) if n else None, int(pts.dtype == torch.float64), n, cols,
                                                   _ptr(radius), _ptr(rgb), _ptr(stats10), int(id_base), ctypes.byref(cam),
                                                   ctypes.byref(style), _stream_ptr(stream)))

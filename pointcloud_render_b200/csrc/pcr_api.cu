@@ -777,6 +777,34 @@ int pcr_render(pcr_ctx* ctx, const float* d_pos, const float* d_attr, int64_t n,
     return leave(ctx, s);
 }
 
+int pcr_render_transformed(pcr_ctx* ctx, const float* d_pcl, int64_t n, int cols, const float* d_radius, const float* d_rgb,
+                           const pcr_camera* cam, const pcr_style* style, uint64_t* d_vis, uint8_t* d_rgba, void* stream)
+{
+    int rc = check_common(ctx, n, cols, style);
+    if (rc) return rc;
+    if (!cam || !d_rgba || (n > 0 && !d_pcl)) return fail(ctx, PCR_ERR_INVALID, "pcr_render_transformed: NULL buffer");
+    if (style->trails != 0 && style->trails != 1) return fail(ctx, PCR_ERR_INVALID, "pcr_render_transformed: trails must be 0 or 1");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!d_vis) { rc = ensure_vis(ctx); if (rc) return rc; }
+    if ((rc = enter(ctx, s))) return rc;
+    if ((rc = upload_frames(ctx, cam, 1, s))) return rc;
+    // the frame is used as it is: centre 0 and scale 1 make K1's (x - c) / s exact, xform = 1 skips the axis transform;
+    // the cloud's min / max (position colormap) are still taken from the data
+    if (n > 0) {
+        rc = launch_stats(ctx, d_pcl, 0, n, cols, 0, 1, ctx->partials, ctx->stats, 1, s, PCR_MEAN_F64);
+        if (rc) return rc;
+    }
+    LAUNCH(KID_STATS, s, k_stats_identity<<<1, 32, 0, s>>>(ctx->stats, n > 0 ? 1 : 0));
+    StyleDev st = to_style_dev(style);
+    st.xform = 1;
+    const RawSrc raw = {d_pcl, 0, n * cols, cols, ctx->stats, d_radius, d_rgb};
+    const long long px = (long long)cam->width * cam->height;
+    rc = launch_render(ctx, nullptr, nullptr, 0, &raw, n, 1, 0u, st, cam->width, cam->height, d_vis ? d_vis : ctx->vis, px, d_rgba, px, 0, s);
+    if (rc) return rc;
+    return leave(ctx, s);
+}
+
 int pcr_shade(pcr_ctx* ctx, const uint64_t* d_vis, const float* d_pos, const float* d_attr, int64_t n, uint32_t id_base,
               int owner_only, const pcr_camera* cam, const pcr_style* style, uint8_t* d_rgba, void* stream)
 {

@@ -52,6 +52,61 @@ def droplet_faces():
     return np.asarray(f, np.int32)
 
 
+def load_ring_mesh_obj(path, tol=2e-6):
+    """A caller-supplied droplet OBJ (`droplet_mesh_path`, traj_renderer.py:93-99) -> (verts float32 ring-major,
+    n_rings, n_segments) for pcr_set_droplet_mesh.  The device raster derives the faces from the ring structure and
+    the shading normals from the ring profile, so the file must be what _create_droplet_mesh writes for SOME
+    (n_rings, n_segments, profile): (n_rings+1) rings of n_segments vertices on circles about the z axis, vertex 0 of
+    every ring in the xz half-plane, ring z strictly decreasing (pole rings may coincide with the poles), and the
+    reference's face list (v0,v2,v1),(v1,v2,v3) per quad.  Anything else raises ValueError: there is no silent
+    fallback to the built-in mesh."""
+    verts, faces = [], []
+    with open(path) as f:
+        for line in f:
+            tok = line.split()
+            if not tok:
+                continue
+            if tok[0] == "v":
+                verts.append([float(tok[1]), float(tok[2]), float(tok[3])])
+            elif tok[0] == "f":
+                idx = [int(t.split("/")[0]) - 1 for t in tok[1:]]
+                if len(idx) != 3:
+                    raise ValueError(f"{path}: only triangle faces are supported")
+                faces.append(idx)
+    if not verts or not faces:
+        raise ValueError(f"{path}: no vertices / faces")
+    n_seg = faces[0][1] - faces[0][0]                      # first face is (0, n_segments, 1)
+    if n_seg < 3 or len(verts) % n_seg or len(verts) // n_seg < 2:
+        raise ValueError(f"{path}: not a ring-structured mesh (cannot infer the ring size from the first face)")
+    n_rings = len(verts) // n_seg - 1
+    want = []
+    for i in range(n_rings):
+        for j in range(n_seg):
+            v0, v1 = i * n_seg + j, i * n_seg + (j + 1) % n_seg
+            want += [[v0, v0 + n_seg, v1], [v1, v0 + n_seg, v1 + n_seg]]
+    if faces != want:
+        raise ValueError(f"{path}: faces are not the ring topology (v0,v2,v1),(v1,v2,v3) of _create_droplet_mesh")
+    v = np.asarray(verts, np.float64).reshape(n_rings + 1, n_seg, 3)
+    r = np.hypot(v[:, 0, 0], v[:, 0, 1])
+    phi = 2 * np.pi * np.arange(n_seg) / n_seg
+    ideal = np.stack([r[:, None] * np.cos(phi), r[:, None] * np.sin(phi), np.repeat(v[:, :1, 2], n_seg, 1)], axis=-1)
+    if np.abs(v[:, 0, 1]).max() > tol or np.abs(v - ideal).max() > tol:
+        raise ValueError(f"{path}: rings are not circles about the z axis starting in the xz half-plane (surface of revolution)")
+    if not np.all(np.diff(v[:, 0, 2]) < 0):
+        raise ValueError(f"{path}: ring z must decrease strictly from the first ring to the last")
+    out = np.ascontiguousarray(v.reshape(-1, 3).astype(np.float32))
+    return out, int(n_rings), int(n_seg)
+
+
+def write_obj(path, verts, faces):
+    """The OBJ text _create_droplet_mesh writes (6 decimals, 1-based faces) — for callers that want the file."""
+    with open(path, "w") as f:
+        for x, y, z in np.asarray(verts, np.float64):
+            f.write(f"v {x:.6f} {y:.6f} {z:.6f}\n")
+        for a, b, c in np.asarray(faces):
+            f.write(f"f {a + 1} {b + 1} {c + 1}\n")
+
+
 _ROT_CACHE = {}
 
 

@@ -84,9 +84,10 @@ class PointCloudRenderer:
     PRESET = "example"
     DEVICE = 0
     WITH_VELOCITY = False            # load_point_cloud reads x,y,z only (example_renderer.py:108-109)
+    TRAILS_DEFAULT = False           # example_renderer.py draws no trails
 
     def __init__(self, file_path, output_folder=None, width=None, height=None, color_mode=_native.COLOR_CONST,
-                 radius=None, user_rgb=None, trails=False):
+                 radius=None, user_rgb=None, trails=None):
         self.file_path = file_path
         self.folder, full_filename = os.path.split(file_path) if file_path else ("", "")
         self.folder = self.folder or '.'
@@ -98,7 +99,9 @@ class PointCloudRenderer:
         self.color_mode = int(color_mode)
         self.radius = radius          # None -> the BALL_SEGMENT literal; float; or per-point array (extension)
         self.user_rgb = user_rgb
-        self.trails = bool(trails)    # draw the script's velocity trails (render_trajectory, 6-column frames)
+        # draw the script's velocity trails for 6-column frames: None = what the script does (the trajectory scripts
+        # always call _add_velocity_trail for an (N,6) cloud, traj_ball_renderer.py:319-324; example_renderer.py never)
+        self.trails = self.TRAILS_DEFAULT if trails is None else bool(trails)
 
     # ---- hooks the reference exposes ----------------------------------------------------
     @staticmethod
@@ -180,12 +183,20 @@ class PointCloudRenderer:
         import torch
         t, _ = _to_device(pcl, self.DEVICE)
         t = t.to(torch.float32)
+        if t.dim() != 2 or t.shape[1] not in (3, 6):
+            raise ValueError("point cloud must be (N,3) or (N,6)")
         n = t.shape[0]
         eng = _engine(self.DEVICE, n, self.width, self.height)
         style = self._style()
         if self.radius is not None and np.ndim(self.radius) == 0:
             style.radius = float(self.radius)
         radius, rgb = self._per_point(n, t.device)
+        cam = self.config.camera(frame_index, total_frames, self.width, self.height)
+        if style.trails == 1 and t.shape[1] == 6:
+            # spheres AND the velocity trail of every point, like generate_xml_content (traj_ball_renderer.py:319-330):
+            # the fused path with the frame taken as it is (pcr_render_transformed)
+            vis, rgba = eng.render_transformed(t, cam, style, radius=radius, rgb=rgb)
+            return RenderedScene(rgba, vis)
         # colour hook + float4 packing without touching the coordinates again (xform = 1 keeps
         # positions as they are; centre 0 / scale 1 are injected so nothing is re-standardised)
         stats = torch.zeros(10, dtype=torch.float64, device=t.device)
@@ -195,7 +206,6 @@ class PointCloudRenderer:
         st1 = self.config.style(color_mode=self.color_mode, xform=1)
         st1.radius = style.radius
         pos4, attr4 = eng.standardize_with_stats(t, st1, stats, radius=radius, rgb=rgb)
-        cam = self.config.camera(frame_index, total_frames, self.width, self.height)
         vis, rgba = eng.render(pos4, attr4, cam, style)
         return RenderedScene(rgba, vis)
 
@@ -240,13 +250,15 @@ class TrajectoryBallRenderer(PointCloudRenderer):
     """traj_ball_renderer.py:80 — per-frame sphere render with an animated camera."""
     PRESET = "traj_ball"
     WITH_VELOCITY = True
+    TRAILS_DEFAULT = True            # _add_velocity_trail for every point of an (N,6) cloud (traj_ball_renderer.py:319-324)
 
     @staticmethod
     def compute_color():
         return np.array([0.3, 0.3, 0.3])
 
     def process(self, frame_index=0, total_frames=220):
-        """traj_ball_renderer.py:365-398 (velocity trails: SURVEY.md §8f-1, not drawn yet)."""
+        """traj_ball_renderer.py:365-398.  An (N,6) cloud gets its velocity trails (render_scene -> pcr_render_transformed),
+        as generate_xml_content draws them (:319-330); trails=False in the constructor turns them off."""
         pcl = self.load_point_cloud()
         if len(pcl.shape) == 3:
             pcl = pcl[0]
@@ -317,11 +329,15 @@ class _DropletMixin:
     TRAILS = _native.TRAILS_NONE
 
     def __init__(self, file_path, output_folder=None, droplet_mesh_path=None, droplets=True, **kw):
-        # droplet_mesh_path: the reference lets a caller substitute an OBJ file; the mesh here is the built-in
-        # surface of revolution (there is no file), so the argument is accepted and ignored
+        # droplet_mesh_path (traj_renderer.py:93-99): a caller-supplied OBJ replaces the built-in droplet.  It must be
+        # a ring-structured surface of revolution (droplets.load_ring_mesh_obj raises otherwise — never silently ignored)
         super().__init__(file_path, output_folder=output_folder, **kw)
         self.droplets = bool(droplets)
         self.droplet_mesh_path = droplet_mesh_path
+        self._mesh = None
+        if droplet_mesh_path is not None:
+            from . import droplets as _d
+            self._mesh = _d.load_ring_mesh_obj(droplet_mesh_path)
         self.curve_files = []           # the reference's temp curve files: none are written any more
 
     @staticmethod
@@ -351,8 +367,11 @@ class _DropletMixin:
     def _droplet_engine(self, n, batch=1):
         from . import droplets
         eng = _engine(self.DEVICE, n, self.width, self.height, batch=batch)
-        if getattr(eng, "droplet_mesh", None) != (droplets.N_RINGS, droplets.N_SEGMENTS):
-            eng.set_droplet_mesh(droplets.droplet_vertices(), droplets.N_RINGS, droplets.N_SEGMENTS)
+        verts, rings, segs = self._mesh if self._mesh is not None else (droplets.droplet_vertices(), droplets.N_RINGS, droplets.N_SEGMENTS)
+        key = (rings, segs, hash(verts.tobytes()))
+        if getattr(eng, "droplet_mesh_key", None) != key:
+            eng.set_droplet_mesh(verts, rings, segs)
+            eng.droplet_mesh_key = key
         return eng
 
     def _rotations(self, n, cols, device):

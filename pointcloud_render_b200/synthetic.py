@@ -21,9 +21,7 @@ CONFIGS = {
 }
 
 
-def cloud(n, shape="gauss", seed=0, dtype=np.float32):
-    """(n,3) cloud: 'gauss' = standard normal, 'cube' = uniform [0,1)^3, 'shell' = thin sphere surface."""
-    rng = np.random.default_rng(seed)
+def _cloud(rng, n, shape):
     if shape == "gauss":
         p = rng.standard_normal((n, 3))
     elif shape == "cube":
@@ -34,15 +32,20 @@ def cloud(n, shape="gauss", seed=0, dtype=np.float32):
         p = g * (1.0 + 0.02 * rng.standard_normal((n, 1)))
     else:
         raise ValueError(shape)
-    return np.ascontiguousarray(p, dtype=dtype)
+    return p
+
+
+def cloud(n, shape="gauss", seed=0, dtype=np.float32):
+    """(n,3) cloud: 'gauss' = standard normal, 'cube' = uniform [0,1)^3, 'shell' = thin sphere surface."""
+    return np.ascontiguousarray(_cloud(np.random.default_rng(seed), n, shape), dtype=dtype)
 
 
 def trajectory(frames, n, cols=6, shape="gauss", seed=0, dt=0.01, dtype=np.float32):
     """(frames, n, cols) ballistic trajectory: P_f = P_0 + f dt V + 0.5 (f dt)^2 g, V = 3 N(0,1),
     g = (0,-1,0) in input axes; velocity columns = V + f dt g (cols == 6)."""
     rng = np.random.default_rng(seed)
-    p0 = cloud(n, shape, seed, np.float64)
-    v = 3.0 * rng.standard_normal((n, 3))
+    p0 = _cloud(rng, n, shape)                    # P0 (== cloud(n, shape, seed)) and V come from ONE generator,
+    v = 3.0 * rng.standard_normal((n, 3))         # so V is independent of P0
     g = np.array([0.0, -1.0, 0.0])
     out = np.empty((frames, n, cols), dtype=dtype)
     for f in range(frames):

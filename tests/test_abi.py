@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in pcr.h but not exported"
     assert sorted(_native.SYMBOLS) == declared
-    assert lib.pcr_abi_version() == 3
+    assert lib.pcr_abi_version() == 4
 
 
 def test_struct_layouts_match_header(lib, tmp_path):

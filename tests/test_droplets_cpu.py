@@ -144,3 +144,45 @@ def test_ring_profile_normals():
     # on the spherical cap the smooth normal is radial: (sin theta, cos theta)
     th = np.pi * np.arange(1, 5) / 16
     np.testing.assert_allclose(prof[1:5, 2:], np.stack([np.sin(th), np.cos(th)], 1), atol=2e-3)
+
+
+def test_droplet_mesh_path_is_loaded_or_rejected(tmp_path):
+    """droplet_mesh_path (traj_renderer.py:93-99): an OBJ with the ring structure of _create_droplet_mesh is loaded
+    for pcr_set_droplet_mesh; anything else raises — it is never silently ignored."""
+    from pointcloud_render_b200 import droplets
+    verts, faces = droplets.droplet_vertices(), droplets.droplet_faces()
+    good = tmp_path / "droplet.obj"
+    droplets.write_obj(good, verts, faces)
+    v, rings, segs = droplets.load_ring_mesh_obj(good)
+    assert (rings, segs) == (droplets.N_RINGS, droplets.N_SEGMENTS)
+    np.testing.assert_array_equal(v, verts)
+    # a different surface of revolution with the same topology: a 12 x 8 ellipsoid
+    rows = []
+    for i in range(13):
+        th = np.pi * i / 12
+        for j in range(8):
+            ph = 2 * np.pi * j / 8
+            rows.append([0.01 * np.sin(th) * np.cos(ph), 0.01 * np.sin(th) * np.sin(ph), 0.02 * np.cos(th)])
+    f = []
+    for i in range(12):
+        for j in range(8):
+            v0, v1 = i * 8 + j, i * 8 + (j + 1) % 8
+            f += [[v0, v0 + 8, v1], [v1, v0 + 8, v1 + 8]]
+    other = tmp_path / "ellipsoid.obj"
+    droplets.write_obj(other, rows, f)
+    v2, r2, s2 = droplets.load_ring_mesh_obj(other)
+    assert (r2, s2, v2.shape) == (12, 8, (104, 3)) and v2.dtype == np.float32
+    # not ring structured / not a surface of revolution -> ValueError
+    bad = tmp_path / "bad.obj"
+    bad.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
+    with pytest.raises(ValueError):
+        droplets.load_ring_mesh_obj(bad)
+    skew = np.array(rows)
+    skew[20, 0] += 0.001
+    droplets.write_obj(bad, skew, f)
+    with pytest.raises(ValueError):
+        droplets.load_ring_mesh_obj(bad)
+    from pointcloud_render_b200 import renderers
+    with pytest.raises(ValueError):
+        renderers.TrajectoryRenderer(None, droplet_mesh_path=str(bad))
+    assert renderers.TrajectoryRenderer(None, droplet_mesh_path=str(other))._mesh[1:] == (12, 8)

@@ -572,6 +572,72 @@ def test_float64_frames_with_trails_device_and_host_entries(ctx, orc):
         check_image(rgba[k].cpu().numpy(), img)
 
 
+def test_process_draws_the_velocity_trails_the_reference_draws(tmp_path, lib, orc):
+    """TrajectoryBallRenderer.process() (and the Original/B0/B1 subclasses) must draw what generate_xml_content
+    emits for an (N,6) cloud: one sphere AND one velocity trail per point (traj_ball_renderer.py:319-330,
+    traj_b0.py:117-191).  process() -> render_scene -> pcr_render_transformed; keys bit-exact against the oracle's
+    sphere + capsule caster on the facade's own standardised / transformed array, image within one code value."""
+    from PIL import Image
+    from pointcloud_render_b200 import renderers
+    n, W, H = 3000, 480, 270
+    for cls, preset, frame in ((renderers.TrajectoryBallRenderer, "traj_ball", 57), (renderers.TrajB0Renderer, "traj_b0", 120),
+                               (renderers.FixedFrame199Renderer, "traj_original", 199)):
+        cfg = PRESETS[preset]
+        raw = synthetic.trajectory(1, n, 6, seed=frame)[0]
+        raw[:, 3:] *= 2.0
+        path = tmp_path / f"frame_{frame:04d}_{preset}.npy"
+        np.save(path, raw)
+        r = cls(str(path), output_folder=str(tmp_path / "render"), width=W, height=H)
+        assert r.trails, "the trajectory scripts draw trails by default"
+        pcl = r.transform_coordinates(r.standardize_point_cloud(raw))
+        np.testing.assert_array_equal(pcl, orc.transform_coordinates(orc.standardize_point_cloud(raw), cfg.flip_x))
+        scene = r.render_scene(pcl, frame_index=frame, total_frames=220)
+        pos4 = np.concatenate([pcl[:, :3], np.full((n, 1), cfg.radius, np.float32)], axis=1)
+        fr, sc = orc_frame(orc, cfg, frame, 220, W, H), orc_scene(orc, cfg)
+        tail, head, valid = orc.velocity_trails(pcl, cfg.trail_length_scale(frame))
+        want = orc.add_trails(orc.visibility(pos4, fr, sc), tail, head, valid, fr, n, radius=cfg.trail_radius)
+        np.testing.assert_array_equal(keys(scene.vis), want)
+        ids = scene.point_ids()
+        assert np.any((ids >= n) & (ids < 2 * n)), "process() must show trail ids (n + point)"
+        img = orc.shade_trails(orc.shade(want, pos4, orc.compute_color(pcl, mode=0), fr, sc), want, tail, head, valid, fr, sc, n,
+                               radius=cfg.trail_radius, rgb=cfg.trail_rgb)
+        check_image(scene.numpy(), img)
+        # the file process() writes is that image
+        r.process(frame_index=frame, total_frames=220)
+        np.testing.assert_array_equal(np.asarray(Image.open(tmp_path / "render" / f"frame_{frame:04d}_{preset}.png")), scene.numpy()[..., :3])
+        # trails=False (or a 3-column cloud) draws spheres only
+        off = cls(str(path), width=W, height=H, trails=False).render_scene(pcl, frame_index=frame, total_frames=220)
+        np.testing.assert_array_equal(keys(off.vis), orc.visibility(pos4, fr, sc))
+        three = r.render_scene(pcl[:, :3].copy(), frame_index=frame, total_frames=220)
+        np.testing.assert_array_equal(keys(three.vis), orc.visibility(pos4, fr, sc))
+    renderers.release_engines()
+
+
+def test_wrappers_reject_wrong_dtype_layout_and_device(ctx):
+    """The ctypes wrappers hand raw pointers to C: a strided view, a half / int tensor or a CPU tensor must raise,
+    not be reinterpreted."""
+    cfg = PRESETS["traj_ball"]
+    style, cam = cfg.style(), cfg.camera(0, 220, 64, 48)
+    six = torch.zeros((100, 6), dtype=torch.float32, device="cuda")
+    with pytest.raises(ValueError):
+        ctx.standardize(six[:, :3], style)                                  # non-contiguous slice of an (N,6) tensor
+    with pytest.raises(TypeError):
+        ctx.standardize(six.half(), style)
+    with pytest.raises(TypeError):
+        ctx.render_frames(torch.zeros((1, 100, 3), dtype=torch.int32, device="cuda"), [cam], style)
+    with pytest.raises(ValueError):
+        ctx.render_frames(torch.zeros((1, 100, 3), dtype=torch.float32), [cam], style)      # CPU tensor in the device entry
+    with pytest.raises(ValueError):
+        ctx.render_frames_host(torch.zeros((1, 100, 3), dtype=torch.float32, device="cuda"), [cam], style)
+    with pytest.raises(ValueError):
+        ctx.render_frames(torch.zeros((1, 100, 3), dtype=torch.float32, device="cuda"), [cam], style,
+                          radius=torch.zeros(99, dtype=torch.float32, device="cuda"))
+    with pytest.raises(ValueError):
+        ctx.stats_partial(torch.zeros((100, 4), dtype=torch.float32, device="cuda"))
+    with pytest.raises(ValueError):
+        ctx.render_shard(six, torch.zeros(9, dtype=torch.float64, device="cuda"), cam, style)
+
+
 def test_zero_frames_and_tiny_inputs(ctx):
     cfg = PRESETS["traj_ball"]
     empty = torch.empty((0, 100, 3), dtype=torch.float32, device="cuda")

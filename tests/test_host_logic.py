@@ -110,6 +110,13 @@ def test_synthetic_is_seeded_and_shaped():
     t = synthetic.trajectory(4, 50, 6)
     assert t.shape == (4, 50, 6) and t.dtype == np.float32
     np.testing.assert_allclose(t[3, :, 4] - t[0, :, 4], -0.03, atol=1e-5)      # gravity on the input y axis
+    # P0 and V come from one generator: frame 0 is cloud(n, seed) and V is NOT a multiple of P0 (a radial
+    # expansion would be removed by the per-frame standardisation: every frame the same cloud, only radial trails)
+    big = synthetic.trajectory(2, 4000, 6, seed=5)
+    np.testing.assert_array_equal(big[0, :, :3], synthetic.cloud(4000, "gauss", 5))
+    p0, v = big[0, :, :3].astype(np.float64), big[0, :, 3:].astype(np.float64)
+    cos = np.abs((p0 * v).sum(1)) / (np.linalg.norm(p0, axis=1) * np.linalg.norm(v, axis=1))
+    assert cos.mean() < 0.6 and abs(np.corrcoef(p0[:, 0], v[:, 0])[0, 1]) < 0.1
     r = synthetic.radii(1000)
     assert r.dtype == np.float32 and 0.005 <= r.min() and r.max() <= 0.015
     assert synthetic.CONFIGS["H"]["points"] == 1_000_000 and synthetic.CONFIGS["H"]["width"] == 1024
