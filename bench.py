@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--trails", action="store_true", help="also draw the reference's velocity trails (6-column workloads C3/C4)")
     ap.add_argument("--merge", default="fused", choices=["fused", "nccl"],
                     help="C5 on several GPUs: z-merge fused into the raster over peer memory (default) or NCCL min all-reduce")
+    ap.add_argument("--mean", default="auto", choices=["auto", "f64"],
+                    help="standardisation centre: auto = the reference's sequential np.mean (default), f64 = parallel float64 sums")
+    ap.add_argument("--no-lookahead", action="store_true", help="do not hint the next steps' frames (pcr_prefetch_frames)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with events in the timed region")
@@ -67,34 +70,50 @@ def workload_spec(name, frames_per_step):
     return c
 
 
-def config_dict(name, spec, ring, n_gpus):
+SCHEDULE_STRIDE = 37          # coprime with the schedule lengths: consecutive ring slots jump across the camera schedule
+
+
+def config_dict(name, spec, ring, n_gpus, trails=False, mean="auto"):
+    """The SAME dict from both arms (--impl ours / reference): what is rendered, not how."""
     return {"workload": f"{name}: {spec['points']} points/frame, {spec['width']}x{spec['height']}, preset {spec['preset']}, "
                         f"{spec['cols']} cols f32, colour mode {spec['color_mode']}" + (", per-point radius" if spec["radii"] else ""),
             "points": spec["points"], "width": spec["width"], "height": spec["height"],
             "frames_per_step_per_gpu": spec["frames_per_step"], "resident_ring_frames": ring,
+            "camera_schedule": f"ring slot i = trajectory frame (and camera index) ({SCHEDULE_STRIDE}*i) mod {spec['frames']} of the "
+                               f"{spec['frames']}-frame schedule: every step mixes far, middle and nearest cameras, all indices are visited",
+            "mean_mode": "sequential float32 np.mean of the reference (PCR_MEAN_AUTO)" if mean == "auto" else "parallel float64 sums (PCR_MEAN_F64)",
+            "trails": bool(trails),
             "l2_policy": "inputs larger than L2: each step reads a different slice of a resident frame ring "
                          f"({ring * spec['input_bytes_per_frame'] / 1e6:.0f} MB) and rewrites {spec['frames_per_step'] * spec['width'] * spec['height'] * 12 / 1e6:.0f} MB of outputs",
             "parallelism": "single GPU" if n_gpus == 1 else f"frames sharded over {n_gpus} GPUs, no collective"}
 
 
 def ring_frames(spec, requested=0):
-    """Resident frames per GPU: a multiple of frames_per_step whose inputs exceed the 126 MB L2."""
+    """Resident frames per GPU: a multiple of frames_per_step, at least 4 steps (so that the whole camera schedule is
+    visited and a two-step look-ahead never meets the slice being rendered) whose inputs exceed the 126 MB L2."""
     B = spec["frames_per_step"]
-    ring = requested or max(2 * B, B * int(np.ceil(160e6 / spec["input_bytes_per_frame"] / B)))
+    ring = requested or max(4 * B, B * int(np.ceil(160e6 / spec["input_bytes_per_frame"] / B)))
     return (ring + B - 1) // B * B
 
 
-def make_ring(spec, ring, seed):
-    """`ring` frames of the workload's trajectory (camera/physics frame indices 0..ring-1)."""
+def ring_indices(spec, ring, rank=0):
+    """Trajectory frame (= camera index, as in the reference's main loop: frame f is rendered with camera f) of every
+    ring slot: a stride permutation of the schedule, so every step of 32 consecutive slots spans the whole schedule —
+    the far, cheap cameras and the nearest, most expensive ones alike."""
+    return [(SCHEDULE_STRIDE * (i + 1000 * rank)) % spec["frames"] for i in range(ring)]
+
+
+def make_ring(spec, ring, seed, rank=0):
+    """`ring` frames of the workload's trajectory, slot i = physics frame ring_indices()[i]."""
     from pointcloud_render_b200 import synthetic
-    return synthetic.trajectory(ring, spec["points"], spec["cols"], "gauss", seed=seed)
+    return synthetic.trajectory(ring, spec["points"], spec["cols"], "gauss", seed=seed, frame_indices=ring_indices(spec, ring, rank))
 
 
-def cameras_for(spec, first, count):
+def cameras_for(spec, ring, rank=0):
     from pointcloud_render_b200.presets import PRESETS
     total = spec["frames"]
     cfg = PRESETS[spec["preset"]].for_trajectory(total)
-    return [cfg.camera((first + k) % total, total, spec["width"], spec["height"]) for k in range(count)], cfg
+    return [cfg.camera(f, total, spec["width"], spec["height"]) for f in ring_indices(spec, ring, rank)], cfg
 
 
 # --------------------------------------------------------------------------------------------------
@@ -219,11 +238,12 @@ def cpu_baseline(spec, ring_host, radius, budget_s=12.0, max_frames=40):
     from oracle import pcr_oracle as orc
     from pointcloud_render_b200.presets import PRESETS
     cfg = PRESETS[spec["preset"]].for_trajectory(spec["frames"])
+    idx = ring_indices(spec, len(ring_host))
     orc.set_num_threads()                                       # all host cores, whatever OMP_NUM_THREADS says
-    cpu_frame(orc, ring_host[0], cfg, 0, spec, radius)          # warm-up (page in, OpenMP pool)
+    cpu_frame(orc, ring_host[0], cfg, idx[0], spec, radius)     # warm-up (page in, OpenMP pool)
     total, frames = 0.0, 0
     while frames < max_frames and total < budget_s:
-        total += cpu_frame(orc, ring_host[frames % len(ring_host)], cfg, frames % spec["frames"], spec, radius)
+        total += cpu_frame(orc, ring_host[frames % len(ring_host)], cfg, idx[frames % len(ring_host)], spec, radius)
         frames += 1
     per_pt = xml_emit_seconds_per_point()
     return {"value": frames / total, "unit": "frames/s", "cores": orc.num_threads(), "kind": "port",
@@ -244,26 +264,28 @@ def run_reference(args, spec, rank, world):
     orc.set_num_threads()                                       # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
     cfg = PRESETS[spec["preset"]].for_trajectory(spec["frames"])
     frames_per_step = 2 if spec["points"] >= 500_000 else 4
-    ring = max(4, frames_per_step * 2)
+    ring = 16                                                    # the first 16 slots of the bench ring: same frames, same cameras
     host = make_ring(spec, ring, seed=0)
+    idx = ring_indices(spec, ring)
     from pointcloud_render_b200 import synthetic
     radius = synthetic.radii(spec["points"]) if spec["radii"] else None
     k = 0
     for _ in range(args.warmup):
         for _ in range(frames_per_step):
-            cpu_frame(orc, host[k % ring], cfg, k % spec["frames"], spec, radius); k += 1
+            cpu_frame(orc, host[k % ring], cfg, idx[k % ring], spec, radius); k += 1
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for _ in range(frames_per_step):
-            cpu_frame(orc, host[k % ring], cfg, k % spec["frames"], spec, radius); k += 1
+            cpu_frame(orc, host[k % ring], cfg, idx[k % ring], spec, radius); k += 1
     dt = time.perf_counter() - t0
     fps = args.steps * frames_per_step / dt
-    sample = f"{frames_per_step} frames per step of the same workload, oracle port (numpy + OpenMP C ray caster, 1 ray/pixel)"
+    sample = (f"each step = {frames_per_step} frames of the same workload (a bounded sample of the {spec['frames_per_step']}-frame step; the first "
+              f"{ring} slots of the same ring, same cameras), oracle port (numpy + OpenMP C ray caster, 1 ray/pixel)")
     line = {"impl": "reference", "metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "mpoints_per_s": fps * spec["points"] / 1e6,
-            "config": dict(config_dict(args.workload, spec, ring_frames(spec, args.ring), args.gpus),
-                           reference_sample=f"{frames_per_step} frames per step on the host cores"),
+            "config": config_dict(args.workload, spec, ring_frames(spec, args.ring), args.gpus, trails=bool(args.trails and spec["cols"] == 6), mean=args.mean),
+            "reference_frames_per_step": frames_per_step,
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": orc.num_threads(), "kind": "port", "sample": sample,
                              "host_cpus": os.cpu_count()},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -288,7 +310,9 @@ def run_point_sharded(args, spec, rank, world, local_rank):
     rng = np.random.default_rng(1000 + rank)
     local = torch.from_numpy(rng.standard_normal((b - a, 3)).astype(np.float32)).cuda()   # a Gaussian cloud, shard by shard
     cfg = PRESETS[spec["preset"]]
-    style, cam = cfg.style(color_mode=spec["color_mode"]), cfg.camera(0, 1, W, H)
+    # one cloud split over the ranks: the point-sharded entries take the parallel float64 mean (a float32 fold cannot be
+    # split across shards); the single-GPU run uses the same centre so that 1 vs N GPUs render the same scene
+    style, cam = cfg.style(color_mode=spec["color_mode"], mean_mode=_native.MEAN_F64), cfg.camera(0, 1, W, H)
     ctx = _native.Context(device=local_rank, max_points=b - a, max_w=W, max_h=H, max_batch=1)
 
     bufs = sharding.point_sharded_buffers(b - a, cam, local.device)          # allocated once, reused every frame
@@ -352,6 +376,7 @@ def run_point_sharded(args, spec, rank, world, local_rank):
                 "data": "synthetic", "mpoints_per_s": fps * n / 1e6,
                 "config": {"workload": f"C5: one {n}-point Gaussian cloud at {W}x{H}, preset {spec['preset']}, point-sharded over {world} GPU(s)",
                            "points": n, "width": W, "height": H, "points_per_gpu": b - a,
+                           "mean_mode": "parallel float64 sums (PCR_MEAN_F64: the point-sharded path)",
                            "l2_policy": f"inputs larger than L2 ({(b - a) * 12 / 1e6:.0f} MB of points + {W * H * 8 / 1e6:.0f} MB z-buffer per GPU)",
                            "parallelism": "single GPU" if world == 1 else (
                                f"points sharded over {world} GPUs; z-merge fused into the raster: winners pushed into the row owner's z-buffer with "
@@ -543,21 +568,28 @@ def main():
     ring = ring_frames(spec, args.ring)
     W, H, n = spec["width"], spec["height"], spec["points"]
 
-    host_np = make_ring(spec, ring, seed=rank)                     # every rank renders its own frames
+    host_np = make_ring(spec, ring, seed=rank, rank=rank)          # every rank renders its own frames
     host = torch.from_numpy(host_np).pin_memory()
     resident = host.cuda(non_blocking=True)
     radius_np = synthetic.radii(n) if spec["radii"] else None
     radius = torch.from_numpy(radius_np).cuda() if radius_np is not None else None
     ctx = _native.Context(device=local_rank, max_points=n, max_w=W, max_h=H, max_batch=min(B, args.max_batch))
-    cams_all, cfg = cameras_for(spec, rank * 1000, ring)
-    style = cfg.style(color_mode=spec["color_mode"], trails=args.trails and spec["cols"] == 6)
+    cams_all, cfg = cameras_for(spec, ring, rank)
+    mean_mode = _native.MEAN_F64 if args.mean == "f64" else _native.MEAN_AUTO
+    style = cfg.style(color_mode=spec["color_mode"], trails=args.trails and spec["cols"] == 6, mean_mode=mean_mode)
     rgba = torch.empty((B, H, W, 4), dtype=torch.uint8, device="cuda")
     host_rgba = torch.empty((B, H, W, 4), dtype=torch.uint8).pin_memory()
     slots = ring // B
+    lookahead = 0 if args.no_lookahead else min(2, slots - 1)
 
-    def step_device(s):
+    def step_device(s, cams=None):
+        # K0 of step s + lookahead (statistics incl. the serial reference-exact mean, pre-pass sample) is started now
+        # on side streams — the hint pcr_prefetch_frames; every step issues exactly one, so K steps = K x K0 + K renders
         k = (s % slots) * B
-        ctx.render_frames(resident[k:k + B], cams_all[k:k + B], style, radius=radius, out_rgba=rgba)
+        if lookahead:
+            ka = ((s + lookahead) % slots) * B
+            ctx.prefetch_frames(resident[ka:ka + B], style)
+        ctx.render_frames(resident[k:k + B], cams if cams is not None else cams_all[k:k + B], style, radius=radius, out_rgba=rgba)
 
     def step_host(s):
         k = (s % slots) * B
@@ -576,6 +608,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def timed(n_steps, first, cams_of=None):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for s in range(n_steps):
+            step_device(first + s, cams_of(first + s) if cams_of else None)
+        ev1.record()
+        barrier()
+        return max_over_ranks(ev0.elapsed_time(ev1))
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
 
     # ---------------- device-resident throughput ----------------
@@ -586,22 +628,27 @@ def main():
     if not args.no_profile:
         ctx.profile(True)
     launches0 = ctx.counters()["launches"]
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if sampler:
         sampler.begin()
-    barrier()
-    ev0.record()
-    for s in range(args.steps):
-        step_device(args.warmup + s)
-    ev1.record()
-    barrier()
-    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    dev_ms = timed(args.steps, args.warmup)
     ctx.profile(False)
     prof = ctx.profile_read()
     counters = ctx.counters()
     launches = counters["launches"] - launches0
     frames_total = world * B * args.steps
     fps = frames_total / (dev_ms * 1e-3)
+
+    # the same step with the cameras of one third of the schedule only (far / middle / nearest): what each costs
+    thirds = None
+    if spec["frames"] >= 6 and cfg.eye is None and world == 1:
+        thirds = {}
+        total = spec["frames"]
+        bounds = {"far": (0, total // 3), "middle": (total // 3, 2 * total // 3), "nearest": (2 * total // 3, total)}
+        k3 = max(3, args.steps // 4)
+        for name, (lo, hi) in bounds.items():
+            cams3 = [cfg.camera(lo + (j * 7) % (hi - lo), total, W, H) for j in range(B)]
+            timed(1, 0, lambda s: cams3)
+            thirds[name] = {"camera_indices": [lo, hi - 1], "frames_per_s": B * k3 / (timed(k3, 0, lambda s: cams3) * 1e-3)}
 
     # ---------------- end to end through the host-buffer entry ----------------
     e2e = None
@@ -626,59 +673,94 @@ def main():
         torch.cuda.synchronize()
         h2d_gbs = 3 * B * spec["input_bytes_per_frame"] / (cp0.elapsed_time(cp1) * 1e-3) / 1e9
         del dst
-        e2e = {"value": frames_total / e2e_s, "unit": "frames/s", "pcie_h2d_gbs_measured": h2d_gbs,
-               "h2d_copy_bound_frames_per_s": world * h2d_gbs * 1e9 / spec["input_bytes_per_frame"],
+        h2d_all = [h2d_gbs]
+        if world > 1:
+            t = torch.tensor([h2d_gbs], dtype=torch.float64, device="cuda")
+            g = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(g, t)
+            h2d_all = [float(x.item()) for x in g]
+        e2e = {"value": frames_total / e2e_s, "unit": "frames/s", "pcie_h2d_gbs_measured": h2d_gbs, "pcie_h2d_gbs_per_rank": h2d_all,
+               "h2d_copy_bound_frames_per_s": sum(h2d_all) * 1e9 / spec["input_bytes_per_frame"],
                "h2d_bytes_per_step": int(B * spec["input_bytes_per_frame"] + (n * 4 if spec["radii"] else 0)),
                "d2h_bytes_per_step": int(B * W * H * 4), "ms_per_step": e2e_s / args.steps * 1e3,
                "api": "pcr_render_frames_host (pinned host trajectory in, pinned host RGBA8 out; copies overlap kernels)"}
     if sampler:
         sampler.end()           # the clock record covers both timed regions (device-resident and end-to-end)
         sampler.stop()
+    numa_all = [numa]
+    if world > 1:
+        numa_all = [None] * world
+        dist.all_gather_object(numa_all, numa)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---------------- roofline of the dominant kernel ----------------
+    # ---------------- rooflines ----------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    clocks = sampler.summary() if sampler else None
     roofline = None
     kernels = {}
+    SIDE = ("k_stats", "k_mean_sequential")          # launched on side streams (K0 look-ahead): they overlap the render kernels
     if prof:
-        total_ms = sum(v[0] for v in prof.values())
+        side_active = lookahead > 0
+        inline = {k: v for k, v in prof.items() if not (side_active and k in SIDE)}
+        total_ms = sum(v[0] for v in inline.values())
         for name, (ms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
-            kernels[name] = {"ms_total": round(ms, 4), "launches": int(cnt), "us_per_launch": round(ms / cnt * 1e3, 3),
-                             "share": round(ms / total_ms, 4)}
-        top = max(prof.items(), key=lambda kv: kv[1][0])
+            kernels[name] = {"ms_total": round(ms, 4), "launches": int(cnt), "us_per_launch": round(ms / cnt * 1e3, 3)}
+            if name in inline:
+                kernels[name]["share"] = round(ms / total_ms, 4)
+            else:
+                kernels[name]["overlapped"] = "side stream (look-ahead): runs concurrently with the render kernels, not part of the shares"
+        top = max(inline.items(), key=lambda kv: kv[1][0])
         top_ms, top_cnt = top[1]
         launches_per_step = top_cnt / args.steps
         frames_per_launch = min(B, ctx.max_batch)            # every launch covers one whole internal batch
-        bytes_per_launch = spec["algorithmic_bytes_per_frame"] * frames_per_launch
-        achieved = bytes_per_launch / (top_ms / top_cnt * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.isfile(tpath):              # dram__bytes_read+write per frame of one launch, from the committed ncu capture
-            per_frame = json.load(open(tpath)).get(args.workload, {}).get(top[0], {}).get("dram_bytes_per_frame_per_launch")
+        step_bytes = spec["algorithmic_bytes_per_frame"] * B
+        # the kernel's average launch handles step_bytes / launches_per_step of the step's algorithmic bytes (its
+        # launches share the step: pre-pass + main pass), so achieved = step bytes / (the kernel's time per step)
+        bytes_per_launch = step_bytes / launches_per_step
+        us_per_launch = top_ms / top_cnt * 1e3
+        achieved = bytes_per_launch / (us_per_launch * 1e-6) / 1e9
+        traffic = issue = None
+        cpath = os.path.join(ROOT, "profiles", "ncu_counters.json")
+        if os.path.isfile(cpath):
+            # committed ncu capture of the same command (profiles/): DRAM bytes and warp instructions per frame and launch
+            cj = json.load(open(cpath)).get(args.workload, {})
+            per_frame = cj.get("kernels", {}).get(top[0], {}).get("dram_bytes_per_frame_per_launch")
             traffic = per_frame * frames_per_launch if per_frame else None
+            wi = cj.get("warp_instructions_per_frame")
+            if wi and clocks and clocks.get("sm_mhz"):
+                sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+                issue_peak = sms * 4 * clocks["sm_mhz"] * 1e6                # warp instructions / s: 4 schedulers per SM, 1 per clock
+                issue = {"warp_instructions_per_step": wi * B, "issue_peak_per_s": issue_peak,
+                         "achieved_per_s": wi * B * args.steps / (dev_ms * 1e-3),
+                         "frac": wi * B * args.steps / (dev_ms * 1e-3) / issue_peak,
+                         "source": f"profiles/ncu_counters.json ({cj.get('capture', 'ncu smsp__inst_executed.sum per kernel')}); peak = SMs x 4 schedulers x measured SM clock"}
         roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": bytes_per_launch, "frames_per_launch": frames_per_launch,
-                    "us_per_launch": top_ms / top_cnt * 1e3, "launches_per_step": launches_per_step,
-                    "whole_step_achieved_gbs": spec["algorithmic_bytes_per_frame"] * B * args.steps / (dev_ms * 1e-3) / 1e9,
-                    "whole_step_frac": spec["algorithmic_bytes_per_frame"] * B * args.steps / (dev_ms * 1e-3) / 1e9 / peak,
-                    "note": "algorithmic bytes = N*b_in + W*H*(8+4) per frame (SURVEY.md 8d); the path is bound by sphere-pixel "
-                            "tests, not by HBM bytes"}
+                    "algorithmic_bytes_per_launch": bytes_per_launch, "algorithmic_bytes_per_step": step_bytes,
+                    "frames_per_launch": frames_per_launch, "us_per_launch": us_per_launch, "launches_per_step": launches_per_step,
+                    "whole_step_achieved_gbs": step_bytes * args.steps / (dev_ms * 1e-3) / 1e9,
+                    "whole_step_frac": step_bytes * args.steps / (dev_ms * 1e-3) / 1e9 / peak,
+                    "issue": issue,
+                    "note": "algorithmic bytes = N*b_in + W*H*(8+4) per frame (SURVEY.md 8d). frac = the step's algorithmic bytes / the top kernel's "
+                            "time per step (all its launches) / peak; whole_step_frac = the same bytes / the whole step. The path is bound by "
+                            "sphere-pixel tests (instruction issue: roofline.issue), not by HBM bytes"}
 
     line = {"metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "mpoints_per_s": fps * n / 1e6,
-            "config": dict(config_dict(args.workload, spec, ring, world), trails=bool(args.trails and spec["cols"] == 6)),
+            "config": config_dict(args.workload, spec, ring, world, trails=bool(args.trails and spec["cols"] == 6), mean=args.mean),
+            "stats_lookahead_steps": lookahead,
             "e2e": e2e, "gpu_launches": int(launches), "kernels": kernels, "roofline": roofline,
-            "clocks": sampler.summary() if sampler else None, "host_placement": numa,
+            "per_schedule_third": thirds,
+            "clocks": clocks, "host_placement": numa_all if world > 1 else numa,
             "pairs_last_frame": counters["pairs_last_frame"], "overflow_frames": counters["overflow_frames"]}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(spec, host_np, radius_np)

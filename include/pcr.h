@@ -117,11 +117,13 @@ typedef struct pcr_style {
 
 /* The reference's np.mean(axis=0) is a SEQUENTIAL sum in the input dtype (example_renderer.py:96),
  * whose float32 rounding error grows with N.  PCR_MEAN_SEQUENTIAL reproduces it bit for bit (one
- * thread per axis, ~2.4 ms per million points); PCR_MEAN_F64 sums in float64 in parallel and rounds
- * once (order independent, more accurate, not bit-identical to numpy for float32 input);
- * PCR_MEAN_AUTO = sequential up to PCR_MEAN_AUTO_MAX_POINTS points per frame, float64 above. */
+ * thread per axis: ~2 ms of latency per million points, which the whole-path entries hide by computing it for
+ * later batches on side streams while earlier ones render — see pcr_prefetch_frames); PCR_MEAN_F64 sums in float64
+ * in parallel and rounds once (order independent, more accurate, not bit-identical to numpy for float32 input).
+ * PCR_MEAN_AUTO (the default) = the reference's arithmetic wherever one GPU sees the whole frame, i.e. SEQUENTIAL
+ * in every entry that takes whole frames, at any size; only the point-sharded entries (pcr_stats_partial ->
+ * pcr_finalize_stats), where a float fold cannot be split across shards, use the float64 mean. */
 enum { PCR_MEAN_AUTO = 0, PCR_MEAN_SEQUENTIAL = 1, PCR_MEAN_F64 = 2 };
-#define PCR_MEAN_AUTO_MAX_POINTS 131072
 
 /* f32 camera frame derived on the HOST in double precision from a pcr_camera.
  * Kernels and the parity oracle consume exactly these numbers. */
@@ -222,6 +224,18 @@ int pcr_render_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, 
                       int n_frames, const float* d_radius, const float* d_rgb,
                       const pcr_camera* cams, const pcr_style* style,
                       uint64_t* d_vis, uint8_t* d_rgba, void* stream);
+
+/* Hint: the n_frames frames at d_in (as they are once everything already submitted to `stream` has run) will be handed
+ * to pcr_render_frames later, unchanged, with the same n / cols / dtype / style->mean_mode and at the same addresses.
+ * Their K0 products — the standardisation statistics, incl. the serial reference-exact mean (~2 ms of latency per
+ * million points), and the occluder pre-pass sample — are computed NOW on side streams, one per batch, so that they
+ * overlap whatever renders in the meantime (the reference does the same on the host: traj_renderer.py:718-743
+ * standardises every frame before it renders the first).  pcr_render_frames looks its batches up (by address and
+ * shape, max_batch frames at a time) and computes only what nobody prepared; results never depend on hints.  At
+ * most 4 batches are kept (further frames are simply not prefetched; an unconsumed hint is dropped when its slot is
+ * needed).  n_frames == 0 drops every hint.  The caller must not modify hinted frames before rendering them. */
+int pcr_prefetch_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols, int n_frames,
+                        const pcr_style* style, void* stream);
 
 /* Same with HOST buffers: h_in is copied host->device and h_rgba (and h_vis if not NULL)
  * device->host in chunks on two internal streams so copies overlap the kernels.

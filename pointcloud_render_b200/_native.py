@@ -16,8 +16,7 @@ ID_MISS = 0xFFFFFFFF
 KEY_MISS = 0x7F800000FFFFFFFF
 
 COLOR_CONST, COLOR_POSITION, COLOR_VELOCITY, COLOR_USER = 0, 1, 2, 3
-MEAN_AUTO, MEAN_SEQUENTIAL, MEAN_F64 = 0, 1, 2     # pcr_style.mean_mode
-MEAN_AUTO_MAX_POINTS = 131072
+MEAN_AUTO, MEAN_SEQUENTIAL, MEAN_F64 = 0, 1, 2     # pcr_style.mean_mode (AUTO = the reference's sequential mean for whole frames)
 
 # every symbol include/pcr.h declares (tests check the library exports all of them)
 SYMBOLS = (
@@ -27,7 +26,7 @@ SYMBOLS = (
     "pcr_transform_coordinates", "pcr_profile", "pcr_profile_read", "pcr_kernel_name", "pcr_set_occlusion", "pcr_finalize_stats", "pcr_velocity_trails", "pcr_render_shard", "pcr_shade_shard",
     "pcr_set_droplet_mesh", "pcr_droplet_transforms", "pcr_history_trails", "pcr_render_droplet_frames",
     "pcr_peer_alloc", "pcr_ipc_export", "pcr_ipc_open", "pcr_ipc_close", "pcr_peer_set", "pcr_peer_begin_frame",
-    "pcr_render_shard_peer", "pcr_shade_shard_peer", "pcr_selftest_scale_div", "pcr_render_transformed",
+    "pcr_render_shard_peer", "pcr_shade_shard_peer", "pcr_selftest_scale_div", "pcr_render_transformed", "pcr_prefetch_frames",
 )
 HISTORY_FRAMES, MAX_CTRL = 20, 21                   # PCR_HISTORY_FRAMES, PCR_MAX_CTRL
 TRAILS_NONE, TRAILS_VELOCITY, TRAILS_HISTORY = 0, 1, 2
@@ -86,6 +85,7 @@ def load_library():
     L.pcr_shade.argtypes = [vp, vp, vp, vp, i64, u32, i32, camp, styp, vp, vp]
     L.pcr_render_transformed.argtypes = [vp, vp, i64, i32, vp, vp, camp, styp, vp, vp, vp]
     L.pcr_render_frames.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, camp, styp, vp, vp, vp]
+    L.pcr_prefetch_frames.argtypes = [vp, vp, i32, i64, i32, i32, styp, vp]
     L.pcr_render_frames_host.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, camp, styp, vp, vp]
     L.pcr_zmin.argtypes = [vp, vp, vp, i64, vp]
     L.pcr_zmerge_nccl.argtypes = [vp, vp, i64, vp, vp]
@@ -401,6 +401,15 @@ class Context:
                                                _ptr(rgba), _stream_ptr(stream)))
         return (rgba, vis) if (want_vis or out_vis is not None) else rgba
 
+    def prefetch_frames(self, traj, style, stream=None):
+        """Hint (pcr_prefetch_frames): these (F,N,3|6) CUDA frames will be passed to render_frames later, unchanged —
+        their standardisation statistics (incl. the serial reference-exact mean) are computed now on side streams."""
+        import torch
+        _check_points(traj, dims=3, what="traj")
+        F, n, cols = traj.shape
+        self._check(self.lib.pcr_prefetch_frames(self.handle, _ptr(traj) if F else None, int(traj.dtype == torch.float64), n, cols, F,
+                                                 ctypes.byref(style), _stream_ptr(stream)))
+
     def render_frames_host(self, traj_host, cams, style, radius_host=None, rgb_host=None, out_rgba=None, out_vis=None):
         """Host-buffer entry (what a reference script would call): traj_host is a CPU tensor or
         numpy array (F,N,3|6), ideally pinned; returns rgba as a CPU tensor (F,H,W,4).  Synchronous."""
@@ -533,6 +542,16 @@ class Context:
     def zmin_(self, dst, src, stream=None):
         self._check(self.lib.pcr_zmin(self.handle, _ptr(dst), _ptr(src), dst.numel(), _stream_ptr(stream)))
         return dst
+
+    def zmerge_nccl_(self, vis, comm, stream=None):
+        """C1 through the C ABI: in-place ncclAllReduce(uint64, min) of the (H,W) keys over `comm` (sharding.NcclComm
+        or a raw ncclComm_t address)."""
+        import torch
+        _check_vector(vis, vis.numel(), dtype=torch.int64, what="vis")
+        handle = getattr(comm, "comm", comm)
+        handle = handle if isinstance(handle, ctypes.c_void_p) else ctypes.c_void_p(int(handle))
+        self._check(self.lib.pcr_zmerge_nccl(self.handle, _ptr(vis), vis.numel(), handle, _stream_ptr(stream)))
+        return vis
 
     def set_occlusion(self, mode=-1, step=0, min_points=0):
         """Occlusion pre-pass: mode -1 auto, 0 off, 1 always (see pcr_set_occlusion)."""

@@ -23,6 +23,11 @@ namespace {
 
 constexpr int RING_SLOTS = 4;
 constexpr int MAX_STAT_BLOCKS = 1184;   // 148 SMs x 8
+// K0 products (standardisation statistics + the compact pre-pass sample) of up to PREP_SLOTS batches can exist ahead of
+// the batch being rendered; region PREP_SLOTS of the stats scratch belongs to the entries that run K0 in line on the
+// caller's stream (pcr_standardize, pcr_stats_partial, pcr_render_transformed, the droplet path).
+constexpr int PREP_SLOTS = 4;
+constexpr int INLINE_REGION = PREP_SLOTS;
 
 enum KernelId { KID_STATS = 0, KID_TRANSFORM, KID_PROJECT, KID_SCAN, KID_SCATTER, KID_RASTER, KID_HIZ, KID_SHADE,
                 KID_ZMIN, KID_AXIS, KID_FILL, KID_MEAN, KID_LUT, KID_DROP_PREP, KID_FILL_FLOOR, KID_RASTER_POLY, KID_RASTER_DROP,
@@ -69,7 +74,7 @@ struct pcr_ctx {
     void* sample = nullptr;           // [2][max_batch][ceil(n/step)][3] every step-th point of a frame, written by K0 for the pre-pass
     size_t sample_bytes = 0;
     int sample_prepass = 1;           // PCR_SAMPLE_PREPASS=0 disables (diagnostics)
-    int stats_ahead = 1;              // K0 of batch k+1 on a second stream while batch k renders (PCR_STATS_AHEAD=0: in line)
+    int stats_ahead = 1;              // K0 of the next batches on side streams while a batch renders (PCR_STATS_AHEAD=0: in line)
     float4* p_ext = nullptr;          // capsule end B — allocated when the first frames with trails arrive
     int raster_ctas_per_sm[2] = {4, 2};   // k_raster_tiles<false / true>: resident CTAs per SM (occupancy query)
     unsigned long long* stat_pairs = nullptr;
@@ -131,9 +136,20 @@ struct pcr_ctx {
     cudaStream_t last_stream = nullptr;
     bool has_last = false;
 
-    // stats-ahead pipeline of pcr_render_frames: K0 of batch k+1 runs on s_aux while batch k renders
-    cudaStream_t s_aux = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_stats[2] = {}, ev_free[2] = {};
+    // stats-ahead pipeline: K0 — and the serial reference-exact mean, 2 ms per million points of pure latency — of up
+    // to PREP_SLOTS batches runs on side streams (one per slot, so the serial chains of different batches overlap)
+    // while earlier batches render.  A slot is keyed by the batch's device pointer and shape; pcr_render_frames looks
+    // its batches up before computing anything, so a caller (or pcr_render_frames_host, or pcr_prefetch_frames) can
+    // have the statistics of frames it will render later computed now.
+    struct PrepSlot {
+        const void* in = nullptr; int is_f64 = 0; long long n = 0; int cols = 0, nb = 0, mean_mode = 0, sampled = 0, sstep = 0;
+        bool valid = false;           // holds products nobody has consumed yet
+        bool used = false;            // ev_free has been recorded at least once
+        unsigned long long stamp = 0; // age (eviction order of unconsumed hints)
+        cudaStream_t stream = nullptr;
+        cudaEvent_t ev_fork = nullptr, ev_ready = nullptr, ev_free = nullptr;
+    } prep[PREP_SLOTS];
+    unsigned long long prep_stamp = 0;
 
     // per-kernel CUDA-event timing (pcr_profile / pcr_profile_read)
     bool profiling = false;
@@ -301,10 +317,13 @@ int upload_frames(pcr_ctx* ctx, const pcr_camera* cams, int nb, cudaStream_t str
     return PCR_OK;
 }
 
+// region: which copy of the partials / done scratch this launch uses (a prepared-batch slot, or INLINE_REGION)
 int launch_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, long long n, int cols, long long frame_stride,
-                 int nb, double* partials, double* stats, int finalize, cudaStream_t stream, int mean_mode = PCR_MEAN_F64,
+                 int nb, int region, double* stats, int finalize, cudaStream_t stream, int mean_mode = PCR_MEAN_F64,
                  void* sample = nullptr, long long sample_stride = 0, int sample_step = 1)
 {
+    double* partials = ctx->partials + (size_t)region * ctx->max_batch * MAX_STAT_BLOCKS * 9;
+    unsigned int* done = ctx->done + (size_t)region * ctx->max_batch;
     // 32 points per thread: the per-block reduction (f64 shuffles, last-block fold) must not outweigh the streaming
     int blocks = (int)std::min<long long>((n + 256 * 32 - 1) / (256 * 32), MAX_STAT_BLOCKS);
     if ((long long)blocks * nb < 2 * ctx->num_sms)        // few frames: keep every SM busy with smaller chunks
@@ -314,19 +333,111 @@ int launch_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, long long n, int
     // float4 streaming needs 3 columns and every frame base on a 16-byte boundary
     const int vec = !in_is_f64 && cols == 3 && ((uintptr_t)d_in % 16 == 0) && (nb == 1 || (frame_stride * 4) % 16 == 0);
     if (in_is_f64)
-        LAUNCH(KID_STATS, stream, k_stats<double><<<grid, 256, 0, stream>>>((const double*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, ctx->done, finalize, 0,
+        LAUNCH(KID_STATS, stream, k_stats<double><<<grid, 256, 0, stream>>>((const double*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, done, finalize, 0,
                                                                         (double*)sample, sample_stride, (unsigned int)sample_step));
     else
-        LAUNCH(KID_STATS, stream, k_stats<float><<<grid, 256, 0, stream>>>((const float*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, ctx->done, finalize, vec,
+        LAUNCH(KID_STATS, stream, k_stats<float><<<grid, 256, 0, stream>>>((const float*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, done, finalize, vec,
                                                                        (float*)sample, sample_stride, (unsigned int)sample_step));
-    // the reference's own (sequential, input-dtype) mean replaces the f64 one when asked for
-    const bool sequential = finalize == 1 && (mean_mode == PCR_MEAN_SEQUENTIAL || (mean_mode == PCR_MEAN_AUTO && n <= PCR_MEAN_AUTO_MAX_POINTS));
+    // the reference's own (sequential, input-dtype) mean replaces the f64 one unless the caller asked for PCR_MEAN_F64
+    const bool sequential = finalize == 1 && mean_mode != PCR_MEAN_F64;
     if (sequential) {
         if (in_is_f64)
             LAUNCH(KID_MEAN, stream, k_mean_sequential<double><<<nb, 128, 0, stream>>>((const double*)d_in, n, cols, frame_stride, stats));
         else
             LAUNCH(KID_MEAN, stream, k_mean_sequential<float><<<nb, 128, 0, stream>>>((const float*)d_in, n, cols, frame_stride, stats));
     }
+    return PCR_OK;
+}
+
+double* inline_stats(pcr_ctx* ctx) { return ctx->stats + (size_t)INLINE_REGION * ctx->max_batch * 10; }
+double* slot_stats(pcr_ctx* ctx, int slot) { return ctx->stats + (size_t)slot * ctx->max_batch * 10; }
+
+// ---- prepared batches (see pcr_ctx::PrepSlot) ----------------------------------------------------------------------
+// What the occluder pre-pass needs from K0 for frames of n points: every sstep-th point, compact.
+struct SamplePlan { bool sampled; int sstep; long long stride; };          // stride in elements per frame
+SamplePlan sample_plan(const pcr_ctx* ctx, long long n)
+{
+    const bool occl = ctx->occlusion > 0 || (ctx->occlusion < 0 && n >= ctx->occlusion_min_points);
+    SamplePlan sp;
+    sp.sstep = ctx->occlusion_step;
+    sp.sampled = ctx->sample_prepass && occl && n > sp.sstep;
+    sp.stride = sp.sampled ? ((n + sp.sstep - 1) / sp.sstep) * 3 : 0;
+    return sp;
+}
+
+int ensure_sample(pcr_ctx* ctx, const SamplePlan& sp, size_t elem)
+{
+    if (!sp.sampled) return PCR_OK;
+    const size_t need = (size_t)PREP_SLOTS * ((ctx->max_batch * (size_t)sp.stride * elem + 255) & ~(size_t)255);
+    if (ctx->sample_bytes >= need) return PCR_OK;
+    CK(cudaDeviceSynchronize());
+    for (pcr_ctx::PrepSlot& p : ctx->prep) p.valid = false;          // their samples are gone
+    if (ctx->sample) CK(cudaFree(ctx->sample));
+    ctx->sample = nullptr; ctx->sample_bytes = 0;
+    CK(cudaMalloc(&ctx->sample, need));
+    ctx->sample_bytes = need;
+    return PCR_OK;
+}
+
+// (a slot's region starts at a multiple of the allocation's quarter, whatever n is: a hint for frames of one size is
+// never overwritten by the K0 of frames of another size that landed in a different slot)
+char* slot_sample(pcr_ctx* ctx, int slot, const SamplePlan& sp, size_t)
+{
+    return sp.sampled ? (char*)ctx->sample + (size_t)slot * (ctx->sample_bytes / PREP_SLOTS) : nullptr;
+}
+
+int find_prepared(pcr_ctx* ctx, const void* in, int is_f64, long long n, int cols, int nb, int mean_mode, const SamplePlan& sp)
+{
+    for (int k = 0; k < PREP_SLOTS; ++k) {
+        const pcr_ctx::PrepSlot& p = ctx->prep[k];
+        if (p.valid && p.in == in && p.is_f64 == is_f64 && p.n == n && p.cols == cols && p.nb == nb && p.mean_mode == mean_mode &&
+            p.sampled == (int)sp.sampled && p.sstep == sp.sstep)
+            return k;
+    }
+    return -1;
+}
+
+// K0 (+ the serial mean) of one batch into a free slot, ordered after everything `after` holds at this point (the
+// frames may still be in flight there).  on_side: run on the slot's own high-priority stream (so it overlaps whatever
+// `after` does next); otherwise on `after` itself.  Returns the slot through *slot_out.
+int prepare_batch(pcr_ctx* ctx, const void* in, int is_f64, long long n, int cols, int nb, int mean_mode, const SamplePlan& sp,
+                  cudaStream_t after, bool on_side, int* slot_out)
+{
+    int slot = -1;
+    for (int k = 0; k < PREP_SLOTS && slot < 0; ++k) if (!ctx->prep[k].valid) slot = k;
+    if (slot >= 0) {                                   // among the free ones, the one released longest ago
+        for (int k = 0; k < PREP_SLOTS; ++k)
+            if (!ctx->prep[k].valid && ctx->prep[k].stamp < ctx->prep[slot].stamp) slot = k;
+    } else {                                           // every slot holds an unconsumed hint: drop the oldest
+        slot = 0;
+        for (int k = 1; k < PREP_SLOTS; ++k) if (ctx->prep[k].stamp < ctx->prep[slot].stamp) slot = k;
+    }
+    pcr_ctx::PrepSlot& p = ctx->prep[slot];
+    if (!p.ev_ready) {
+        CK(cudaEventCreateWithFlags(&p.ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&p.ev_ready, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&p.ev_free, cudaEventDisableTiming));
+    }
+    cudaStream_t q = after;
+    if (on_side) {
+        if (!p.stream) {
+            int lo = 0, hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CK(cudaStreamCreateWithPriority(&p.stream, cudaStreamNonBlocking, hi));
+        }
+        q = p.stream;
+        CK(cudaEventRecord(p.ev_fork, after));
+        CK(cudaStreamWaitEvent(q, p.ev_fork, 0));
+    }
+    if (p.used) CK(cudaStreamWaitEvent(q, p.ev_free, 0));           // the batch that last used this slot has been rendered
+    const size_t elem = is_f64 ? 8 : 4;
+    int rc = launch_stats(ctx, in, is_f64, n, cols, n * cols, nb, slot, slot_stats(ctx, slot), 1, q, mean_mode,
+                          slot_sample(ctx, slot, sp, elem), sp.stride, sp.sstep);
+    if (rc) return rc;
+    CK(cudaEventRecord(p.ev_ready, q));
+    p.in = in; p.is_f64 = is_f64; p.n = n; p.cols = cols; p.nb = nb; p.mean_mode = mean_mode; p.sampled = sp.sampled; p.sstep = sp.sstep;
+    p.valid = true; p.stamp = ++ctx->prep_stamp;
+    *slot_out = slot;
     return PCR_OK;
 }
 
@@ -604,9 +715,9 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     ALLOC(ctx->rect, sizeof(uint4) * B * N * 2);
     ctx->gx_cap = (int)std::max<long long>(2 * ctx->num_sms * (2048 / BIN_THREADS), (max_points + BIN_THREADS * 4 - 1) / (BIN_THREADS * 4)) + 1;
     ALLOC(ctx->surv_count, sizeof(unsigned int) * B * (size_t)ctx->gx_cap);
-    ALLOC(ctx->partials, sizeof(double) * B * MAX_STAT_BLOCKS * 9);
-    ALLOC(ctx->stats, sizeof(double) * B * 10 * 2);      // double-buffered (stats-ahead pipeline)
-    ALLOC(ctx->done, sizeof(unsigned int) * B);
+    ALLOC(ctx->partials, sizeof(double) * B * MAX_STAT_BLOCKS * 9 * (PREP_SLOTS + 1));   // one region per prepared-batch slot + the in-line one
+    ALLOC(ctx->stats, sizeof(double) * B * 10 * (PREP_SLOTS + 1));
+    ALLOC(ctx->done, sizeof(unsigned int) * B * (PREP_SLOTS + 1));
     ALLOC(ctx->counts, sizeof(unsigned int) * B * Tn);
     ALLOC(ctx->offsets, sizeof(unsigned int) * B * (Tn + 4));   // per-frame stride tiles_cap + 4 keeps uint4 alignment
     ALLOC(ctx->cursor, sizeof(unsigned int) * B * Tn);
@@ -628,7 +739,7 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
 #undef ALLOC
     if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_frames, sizeof(FrameDev) * B * RING_SLOTS);
     if (e == cudaSuccess) e = cudaMemset(ctx->counts, 0, sizeof(unsigned int) * B * Tn);
-    if (e == cudaSuccess) e = cudaMemset(ctx->done, 0, sizeof(unsigned int) * B);
+    if (e == cudaSuccess) e = cudaMemset(ctx->done, 0, sizeof(unsigned int) * B * (PREP_SLOTS + 1));
     if (e == cudaSuccess) e = cudaMemset(ctx->scan_ready, 0, sizeof(unsigned int) * B * (size_t)ctx->scan_stripes);
     if (e == cudaSuccess) e = cudaMemset(ctx->overflow, 0, sizeof(unsigned int) * B);
     if (e == cudaSuccess) e = cudaMemset(ctx->stat_pairs, 0, sizeof(unsigned long long) * (B + 16));
@@ -663,10 +774,11 @@ void pcr_destroy(pcr_ctx* ctx)
     }
     for (ProfRec& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
-    if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
-    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (pcr_ctx::PrepSlot& p : ctx->prep) {
+        if (p.stream) cudaStreamDestroy(p.stream);
+        for (cudaEvent_t ev : {p.ev_fork, p.ev_ready, p.ev_free}) if (ev) cudaEventDestroy(ev);
+    }
     if (ctx->ev_last) cudaEventDestroy(ctx->ev_last);
-    for (int k = 0; k < 2; ++k) { if (ctx->ev_stats[k]) cudaEventDestroy(ctx->ev_stats[k]); if (ctx->ev_free[k]) cudaEventDestroy(ctx->ev_free[k]); }
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
@@ -681,7 +793,7 @@ int pcr_stats_partial(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, 
     if (!d_in || !d_partial9 || n < 1) return fail(ctx, PCR_ERR_INVALID, "pcr_stats_partial: NULL buffer or n < 1");
     CK(cudaSetDevice(ctx->device));
     if ((rc = enter(ctx, (cudaStream_t)stream))) return rc;
-    int rc2 = launch_stats(ctx, d_in, in_is_f64, n, cols, 0, 1, ctx->partials, d_partial9, 2, (cudaStream_t)stream);
+    int rc2 = launch_stats(ctx, d_in, in_is_f64, n, cols, 0, 1, INLINE_REGION, d_partial9, 2, (cudaStream_t)stream);
     if (rc2) return rc2;
     return leave(ctx, (cudaStream_t)stream);
 }
@@ -723,12 +835,13 @@ int pcr_standardize(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, in
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
     if ((rc = enter(ctx, s))) return rc;
-    rc = launch_stats(ctx, d_in, in_is_f64, n, cols, 0, 1, ctx->partials, ctx->stats, 1, s, style->mean_mode);
+    double* stats = inline_stats(ctx);
+    rc = launch_stats(ctx, d_in, in_is_f64, n, cols, 0, 1, INLINE_REGION, stats, 1, s, style->mean_mode);
     if (rc) return rc;
-    rc = launch_transform(ctx, d_in, in_is_f64, n, cols, 0, 1, d_radius, d_rgb, ctx->stats, to_style_dev(style),
+    rc = launch_transform(ctx, d_in, in_is_f64, n, cols, 0, 1, d_radius, d_rgb, stats, to_style_dev(style),
                           (float4*)d_pos_out, (float4*)d_attr_out, (float4*)d_vel_out, 0, s);
     if (rc) return rc;
-    if (d_stats) CK(cudaMemcpyAsync(d_stats, ctx->stats, sizeof(double) * 10, cudaMemcpyDeviceToDevice, s));
+    if (d_stats) CK(cudaMemcpyAsync(d_stats, stats, sizeof(double) * 10, cudaMemcpyDeviceToDevice, s));
     return leave(ctx, s);
 }
 
@@ -791,14 +904,15 @@ int pcr_render_transformed(pcr_ctx* ctx, const float* d_pcl, int64_t n, int cols
     if ((rc = upload_frames(ctx, cam, 1, s))) return rc;
     // the frame is used as it is: centre 0 and scale 1 make K1's (x - c) / s exact, xform = 1 skips the axis transform;
     // the cloud's min / max (position colormap) are still taken from the data
+    double* stats = inline_stats(ctx);
     if (n > 0) {
-        rc = launch_stats(ctx, d_pcl, 0, n, cols, 0, 1, ctx->partials, ctx->stats, 1, s, PCR_MEAN_F64);
+        rc = launch_stats(ctx, d_pcl, 0, n, cols, 0, 1, INLINE_REGION, stats, 1, s, PCR_MEAN_F64);
         if (rc) return rc;
     }
-    LAUNCH(KID_STATS, s, k_stats_identity<<<1, 32, 0, s>>>(ctx->stats, n > 0 ? 1 : 0));
+    LAUNCH(KID_STATS, s, k_stats_identity<<<1, 32, 0, s>>>(stats, n > 0 ? 1 : 0));
     StyleDev st = to_style_dev(style);
     st.xform = 1;
-    const RawSrc raw = {d_pcl, 0, n * cols, cols, ctx->stats, d_radius, d_rgb};
+    const RawSrc raw = {d_pcl, 0, n * cols, cols, stats, d_radius, d_rgb};
     const long long px = (long long)cam->width * cam->height;
     rc = launch_render(ctx, nullptr, nullptr, 0, &raw, n, 1, 0u, st, cam->width, cam->height, d_vis ? d_vis : ctx->vis, px, d_rgba, px, 0, s);
     if (rc) return rc;
@@ -887,79 +1001,79 @@ int pcr_render_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, 
     if ((rc = enter(ctx, s))) return rc;
     const int B = ctx->max_batch;
     const int nbatches = (n_frames + B - 1) / B;
-    // K0 (and the serial reference-exact mean, when selected) of batch k+1 runs on a second stream
-    // while batch k renders; the stats array is double-buffered.  The serial mean is pure latency
-    // (one warp per frame), so it hides completely behind a full batch of render kernels.
-    const bool ahead = nbatches > 1 && ctx->stats_ahead != 0;
-    if (ahead && !ctx->s_aux) {
-        int lo = 0, hi = 0;
-        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CK(cudaStreamCreateWithPriority(&ctx->s_aux, cudaStreamNonBlocking, hi));
-        CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-        for (int k = 0; k < 2; ++k) {
-            CK(cudaEventCreateWithFlags(&ctx->ev_stats[k], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&ctx->ev_free[k], cudaEventDisableTiming));
+    // K0 — and the serial reference-exact mean, 2 ms of pure latency per million points — of the next batches runs on
+    // side streams while a batch renders: every batch is looked up among the prepared slots first (an earlier
+    // pcr_prefetch_frames, pcr_render_frames_host, or this loop's own look-ahead), and only computed in line when nobody did.
+    const bool ahead = ctx->stats_ahead != 0;
+    const SamplePlan sp = sample_plan(ctx, n);
+    if ((rc = ensure_sample(ctx, sp, elem))) return rc;
+    auto batch_in = [&](int k) { return (const char*)d_in + (size_t)k * B * frame_stride * elem; };
+    auto batch_nb = [&](int k) { return std::min(B, n_frames - k * B); };
+    auto look_ahead = [&](int from) -> int {             // keep up to PREP_SLOTS - 1 later batches in preparation
+        for (int j = from; ahead && j < std::min(nbatches, from + PREP_SLOTS - 1); ++j) {
+            if (find_prepared(ctx, batch_in(j), in_is_f64, n, cols, batch_nb(j), style->mean_mode, sp) >= 0) continue;
+            int free_slots = 0;
+            for (const pcr_ctx::PrepSlot& p : ctx->prep) free_slots += !p.valid;
+            if (!free_slots) break;                      // never evict what this very call still needs
+            int slot;
+            int rc2 = prepare_batch(ctx, batch_in(j), in_is_f64, n, cols, batch_nb(j), style->mean_mode, sp, s, true, &slot);
+            if (rc2) return rc2;
         }
-    }
-    // occluder pre-pass ahead (same condition as launch_render): K0 also writes the compact sample it will read
-    const bool occl = ctx->occlusion > 0 || (ctx->occlusion < 0 && n >= ctx->occlusion_min_points);
-    const int sstep = ctx->occlusion_step;
-    const bool sampled = ctx->sample_prepass && occl && n > sstep;
-    const long long sample_stride = sampled ? ((n + sstep - 1) / sstep) * 3 : 0;          // elements per frame
-    if (sampled) {
-        const size_t need = 2 * (size_t)B * (size_t)sample_stride * elem;
-        if (ctx->sample_bytes < need) {
-            CK(cudaDeviceSynchronize());
-            if (ctx->sample) CK(cudaFree(ctx->sample));
-            ctx->sample = nullptr; ctx->sample_bytes = 0;
-            CK(cudaMalloc(&ctx->sample, need));
-            ctx->sample_bytes = need;
-        }
-    }
-    auto sample_of = [&](int k) -> char* { return sampled ? (char*)ctx->sample + (size_t)(k & 1) * B * (size_t)sample_stride * elem : nullptr; };
-    auto stats_of = [&](int k, cudaStream_t q) -> int {
-        const int f0 = k * B, nb = std::min(B, n_frames - f0);
-        const char* in = (const char*)d_in + (size_t)f0 * frame_stride * elem;
-        return launch_stats(ctx, in, in_is_f64, n, cols, frame_stride, nb, ctx->partials, ctx->stats + (size_t)(k & 1) * B * 10, 1, q,
-                            style->mean_mode, sample_of(k), sample_stride, sstep);
+        return PCR_OK;
     };
-    if (ahead) {
-        CK(cudaEventRecord(ctx->ev_fork, s));                       // the input may still be in flight on the caller's stream
-        CK(cudaStreamWaitEvent(ctx->s_aux, ctx->ev_fork, 0));
-        rc = stats_of(0, ctx->s_aux);
-        if (rc) return rc;
-        CK(cudaEventRecord(ctx->ev_stats[0], ctx->s_aux));
-    }
     for (int k = 0; k < nbatches; ++k) {
         const int f0 = k * B;
-        const int nb = std::min(B, n_frames - f0);
+        const int nb = batch_nb(k);
         rc = upload_frames(ctx, cams + f0, nb, s);
         if (rc) return rc;
-        const char* in = (const char*)d_in + (size_t)f0 * frame_stride * elem;
-        double* stats = ctx->stats + (size_t)(k & 1) * B * 10;
-        if (ahead) {
-            CK(cudaStreamWaitEvent(s, ctx->ev_stats[k & 1], 0));
-            if (k + 1 < nbatches) {
-                if (k >= 1) CK(cudaStreamWaitEvent(ctx->s_aux, ctx->ev_free[(k + 1) & 1], 0));   // batch k-1 has released that buffer
-                rc = stats_of(k + 1, ctx->s_aux);
-                if (rc) return rc;
-                CK(cudaEventRecord(ctx->ev_stats[(k + 1) & 1], ctx->s_aux));
-            }
-        } else {
-            rc = stats_of(k, s);
+        int slot = find_prepared(ctx, batch_in(k), in_is_f64, n, cols, nb, style->mean_mode, sp);
+        if (slot < 0) {
+            // nobody prepared this batch: on a side stream when more batches follow (their K0 then overlaps this one's
+            // render), in line otherwise
+            rc = prepare_batch(ctx, batch_in(k), in_is_f64, n, cols, nb, style->mean_mode, sp, s, ahead && nbatches > 1, &slot);
             if (rc) return rc;
         }
+        if ((rc = look_ahead(k + 1))) return rc;
+        pcr_ctx::PrepSlot& ps = ctx->prep[slot];
+        CK(cudaStreamWaitEvent(s, ps.ev_ready, 0));
         // no K1 launch: K2a and K4 evaluate standardise/transform/colour from the raw frames on the fly
-        RawSrc raw = {in, in_is_f64, frame_stride, cols, stats, d_radius, d_rgb};
-        raw.sample = sample_of(k); raw.sample_stride = sample_stride;
+        RawSrc raw = {batch_in(k), in_is_f64, frame_stride, cols, slot_stats(ctx, slot), d_radius, d_rgb};
+        raw.sample = slot_sample(ctx, slot, sp, elem); raw.sample_stride = sp.stride;
         uint64_t* vis = d_vis ? d_vis + (size_t)f0 * px : ctx->vis;
         const long long vis_stride = d_vis ? px : (long long)ctx->max_w * ctx->max_h;
         rc = launch_render(ctx, nullptr, nullptr, 0, &raw, n, nb, 0u, st, W, H, vis, vis_stride,
                            d_rgba + (size_t)f0 * px * 4, px, 0, s);
         if (rc) return rc;
-        if (ahead) CK(cudaEventRecord(ctx->ev_free[k & 1], s));
+        CK(cudaEventRecord(ps.ev_free, s));
+        ps.valid = false; ps.used = true; ps.stamp = ++ctx->prep_stamp;
     }
     return leave(ctx, s);
+}
+
+int pcr_prefetch_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols, int n_frames, const pcr_style* style, void* stream)
+{
+    int rc = check_common(ctx, n, cols, style);
+    if (rc) return rc;
+    if (n_frames < 0 || (n_frames > 0 && (!d_in || n < 1))) return fail(ctx, PCR_ERR_INVALID, "pcr_prefetch_frames: NULL buffer or empty frames");
+    if (n_frames == 0) {                                  // drop every hint
+        for (pcr_ctx::PrepSlot& p : ctx->prep) p.valid = false;
+        return PCR_OK;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t elem = in_is_f64 ? 8 : 4;
+    const SamplePlan sp = sample_plan(ctx, n);
+    if ((rc = ensure_sample(ctx, sp, elem))) return rc;
+    const int B = ctx->max_batch;
+    const int nbatches = std::min((n_frames + B - 1) / B, PREP_SLOTS);       // a hint: what does not fit is computed later
+    for (int k = 0; k < nbatches; ++k) {
+        const char* in = (const char*)d_in + (size_t)k * B * (size_t)(n * cols) * elem;
+        const int nb = std::min(B, n_frames - k * B);
+        if (find_prepared(ctx, in, in_is_f64, n, cols, nb, style->mean_mode, sp) >= 0) continue;
+        int slot;
+        if ((rc = prepare_batch(ctx, in, in_is_f64, n, cols, nb, style->mean_mode, sp, s, ctx->stats_ahead != 0, &slot))) return rc;
+    }
+    return PCR_OK;
 }
 
 int pcr_render_frames_host(pcr_ctx* ctx, const void* h_in, int in_is_f64, int64_t n, int cols, int n_frames, const float* h_radius,
@@ -1019,6 +1133,9 @@ int pcr_render_frames_host(pcr_ctx* ctx, const void* h_in, int in_is_f64, int64_
         CK(cudaMemcpyAsync(ctx->stage_in[k], (const char*)h_in + (size_t)f0 * frame_bytes, (size_t)nb * frame_bytes,
                            cudaMemcpyHostToDevice, ctx->s_h2d));
         CK(cudaEventRecord(ctx->ev_h2d[k], ctx->s_h2d));
+        // K0 (+ the serial reference-exact mean) of this chunk starts the moment its bytes have landed, on a side
+        // stream: it overlaps the previous chunk's kernels instead of delaying this chunk's
+        if ((rc = pcr_prefetch_frames(ctx, ctx->stage_in[k], in_is_f64, n, cols, nb, style, ctx->s_h2d))) return rc;
         CK(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_h2d[k], 0));
         if (chunk >= 2) CK(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_d2h[k], 0));  // output slot drained
         rc = pcr_render_frames(ctx, ctx->stage_in[k], in_is_f64, n, cols, nb, d_radius, d_rgb, cams + f0, style,
@@ -1318,7 +1435,7 @@ int pcr_render_droplet_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int
         LAUNCH(KID_STATS, s, k_identity_stats<<<(total + 127) / 128, 128, 0, s>>>(ctx->dstats, total));
     for (int g = first_used; g < total && !prestandardised; g += B) {
         const int nb = std::min(B, total - g);
-        rc = launch_stats(ctx, (const char*)d_in + (size_t)g * frame_stride * elem, in_is_f64, n, cols, frame_stride, nb, ctx->partials,
+        rc = launch_stats(ctx, (const char*)d_in + (size_t)g * frame_stride * elem, in_is_f64, n, cols, frame_stride, nb, INLINE_REGION,
                           ctx->dstats + (size_t)g * 10, 1, s, style->mean_mode);
         if (rc) return rc;
     }

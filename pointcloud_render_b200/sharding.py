@@ -88,6 +88,69 @@ def zmerge_(vis, group=None):
     return vis
 
 
+class NcclComm:
+    """An ncclComm_t of our own, for the C entry pcr_zmerge_nccl (`ncclAllReduce(ncclUint64, ncclMin)` on the raw keys;
+    torch.distributed does not hand out its communicator).  Created with the NCCL already loaded in this process
+    (torch's): rank 0 draws the ncclUniqueId, `bcast` (a callable taking / returning 128 bytes — e.g. a
+    torch.distributed broadcast on any backend) distributes it, every rank calls ncclCommInitRank.  One rank per GPU."""
+
+    def __init__(self, rank=0, world=1, bcast=None):
+        import ctypes
+        import glob
+        import os
+        import torch
+        cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so*")) + ["libnccl.so.2"]
+        self.lib = None
+        for c in cands:
+            try:
+                self.lib = ctypes.CDLL(c, mode=ctypes.RTLD_GLOBAL)        # global: pcr_zmerge_nccl finds ncclAllReduce with dlsym
+                break
+            except OSError:
+                continue
+        if self.lib is None:
+            raise RuntimeError("libnccl not found")
+
+        class UniqueId(ctypes.Structure):
+            _fields_ = [("internal", ctypes.c_char * 128)]
+        uid = UniqueId()
+        if rank == 0:
+            self._ck(self.lib.ncclGetUniqueId(ctypes.byref(uid)), "ncclGetUniqueId")
+        raw = bytes(ctypes.string_at(ctypes.byref(uid), 128))
+        if world > 1:
+            raw = bcast(raw)
+            ctypes.memmove(ctypes.byref(uid), raw, 128)
+        self.comm = ctypes.c_void_p()
+        self.lib.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, UniqueId, ctypes.c_int]
+        self._ck(self.lib.ncclCommInitRank(ctypes.byref(self.comm), int(world), uid, int(rank)), "ncclCommInitRank")
+        self.rank, self.world = int(rank), int(world)
+
+    @staticmethod
+    def _ck(rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed with ncclResult {rc}")
+
+    @classmethod
+    def from_process_group(cls, group=None):
+        """One communicator over the ranks of a torch.distributed group (the id travels as a 128-byte broadcast)."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+
+        def bcast(raw):
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+            t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+            dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            return bytes(t.cpu().numpy().tobytes())
+        return cls(rank, world, bcast)
+
+    def close(self):
+        import ctypes
+        if getattr(self, "comm", None) and self.comm.value:
+            self.lib.ncclCommDestroy.argtypes = [ctypes.c_void_p]
+            self.lib.ncclCommDestroy(self.comm)
+            self.comm = None
+
+
 def assemble_image_(rgba, group=None):
     """Byte-wise MAX of owner-only shaded images (pcr_shade owner_only=1 writes 0 where the
     winner is not local, and floor/miss pixels only on rank 0)."""
@@ -103,17 +166,22 @@ def point_sharded_buffers(n_local, cam, device):
             "rgba": torch.empty((cam.height, cam.width, 4), dtype=torch.uint8, device=device)}
 
 
-def render_point_sharded(ctx, pts_local, id_base, n_total, cam, style, radius=None, rgb=None, group=None, shade=True, buffers=None):
+def render_point_sharded(ctx, pts_local, id_base, n_total, cam, style, radius=None, rgb=None, group=None, shade=True, buffers=None,
+                         nccl_comm=None):
     """The whole point-sharded path on one rank: K0 partials -> C0 -> K2/K3 (K1 inlined) -> C1 -> K4(owner)
     -> byte MAX.  pts_local: (n_local, 3|6) CUDA tensor, this rank's slice of the n_total-point cloud.
-    Stream-ordered, no host synchronisation."""
+    Stream-ordered, no host synchronisation.  nccl_comm (an NcclComm): C1 through the C entry pcr_zmerge_nccl
+    (ncclAllReduce on the uint64 keys) instead of torch.distributed's int64 all-reduce — same bits."""
     import torch
     b = buffers or {}
     part = ctx.stats_partial(pts_local)
     stats = allgather_stats_device(ctx, part, n_total, pts_local.dtype == torch.float64, group)
     # fused: K1 is evaluated inside K2a (binning) and K4 (winners only); nothing is materialised
     vis = ctx.render_shard(pts_local, stats, cam, style, id_base=id_base, radius=radius, rgb=rgb, out_vis=b.get("vis"))
-    zmerge_(vis, group)
+    if nccl_comm is not None:
+        ctx.zmerge_nccl_(vis, nccl_comm)
+    else:
+        zmerge_(vis, group)
     if not shade:
         return vis, None
     rgba = ctx.shade_shard(vis, pts_local, stats, cam, style, id_base=id_base, owner_only=True, radius=radius, rgb=rgb,

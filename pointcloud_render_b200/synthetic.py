@@ -40,19 +40,22 @@ def cloud(n, shape="gauss", seed=0, dtype=np.float32):
     return np.ascontiguousarray(_cloud(np.random.default_rng(seed), n, shape), dtype=dtype)
 
 
-def trajectory(frames, n, cols=6, shape="gauss", seed=0, dt=0.01, dtype=np.float32):
+def trajectory(frames, n, cols=6, shape="gauss", seed=0, dt=0.01, dtype=np.float32, frame_indices=None):
     """(frames, n, cols) ballistic trajectory: P_f = P_0 + f dt V + 0.5 (f dt)^2 g, V = 3 N(0,1),
-    g = (0,-1,0) in input axes; velocity columns = V + f dt g (cols == 6)."""
+    g = (0,-1,0) in input axes; velocity columns = V + f dt g (cols == 6).  frame_indices: the physics frame f of
+    every returned frame (default 0..frames-1)."""
     rng = np.random.default_rng(seed)
     p0 = _cloud(rng, n, shape)                    # P0 (== cloud(n, shape, seed)) and V come from ONE generator,
     v = 3.0 * rng.standard_normal((n, 3))         # so V is independent of P0
     g = np.array([0.0, -1.0, 0.0])
+    idx = list(range(frames)) if frame_indices is None else [int(f) for f in frame_indices]
+    assert len(idx) == frames
     out = np.empty((frames, n, cols), dtype=dtype)
-    for f in range(frames):
+    for k, f in enumerate(idx):
         t = f * dt
-        out[f, :, :3] = p0 + t * v + 0.5 * t * t * g
+        out[k, :, :3] = p0 + t * v + 0.5 * t * t * g
         if cols == 6:
-            out[f, :, 3:6] = v + t * g
+            out[k, :, 3:6] = v + t * g
     return out
 
 

@@ -1,8 +1,8 @@
 """Parity of the CUDA path (through the C ABI, libpcr.so) with the CPU oracle.  `-m gpu`.
 
 Bars: visibility keys (depth bits | point id) BIT-EXACT; standardised positions BIT-EXACT against
-the reference's numpy arithmetic in mean_mode SEQUENTIAL (the default up to 131072 points per
-frame), and in mean_mode F64 bit-exact against the order-independent definition (mean summed in
+the reference's numpy arithmetic in mean_mode SEQUENTIAL (= AUTO, the default, at every size),
+and in mean_mode F64 bit-exact against the order-independent definition (mean summed in
 f64, rounded once) and within ref_atol() of the reference; velocities / min / max / scale exact;
 sRGB8 images within 1 code value and PSNR >= 50 dB of the oracle's f64 evaluation of the same
 shading model."""
@@ -336,14 +336,14 @@ def test_headline_size_properties(ctx, orc):
     cfg = PRESETS["traj_ball"].for_trajectory(100)
     x = synthetic.trajectory(1, n, 3, seed=0)[0]
     style = cfg.style()
-    # 1 M points: the default (AUTO) takes the parallel f64 mean; the reference-exact sequential mode
-    # is still available and bit-identical to numpy
-    seq = ctx.standardize(dev(x), cfg.style(mean_mode=_native.MEAN_SEQUENTIAL))[0].cpu().numpy()
-    np.testing.assert_array_equal(seq[:, :3], orc.transform_coordinates(orc.standardize_point_cloud(x), cfg.flip_x))
+    # 1 M points: the default (AUTO) is the reference's own sequential float32 mean, bit-identical to numpy; the
+    # parallel f64 mean is the order-independent definition, within the REFERENCE's summation error of it
     pos4, attr4 = ctx.standardize(dev(x), style)
-    np.testing.assert_array_equal(pos4.cpu().numpy()[:, :3],
-                                  orc.transform_coordinates(orc.standardize_point_cloud(x, exact_mean=True), cfg.flip_x))
-    np.testing.assert_allclose(pos4.cpu().numpy()[:, :3], seq[:, :3], rtol=0, atol=ref_atol(x))
+    seq = pos4.cpu().numpy()
+    np.testing.assert_array_equal(seq[:, :3], orc.transform_coordinates(orc.standardize_point_cloud(x), cfg.flip_x))
+    f64 = ctx.standardize(dev(x), cfg.style(mean_mode=_native.MEAN_F64))[0].cpu().numpy()
+    np.testing.assert_array_equal(f64[:, :3], orc.transform_coordinates(orc.standardize_point_cloud(x, exact_mean=True), cfg.flip_x))
+    np.testing.assert_allclose(f64[:, :3], seq[:, :3], rtol=0, atol=ref_atol(x))
     for frame_index in (0, 99):
         cam = cfg.camera(frame_index, 100, W, H)
         vis, rgba = ctx.render(pos4, attr4, cam, style)
@@ -354,6 +354,92 @@ def test_headline_size_properties(ctx, orc):
         ids = _native.keys_to_ids(vis)
         assert np.all((ids < n) | (ids >= 0xFFFFFFFE))
         assert ctx.counters()["overflow_frames"] == 0
+
+
+def test_fused_headline_batches_match_oracle_on_reference_centres(lib, orc):
+    """The configuration the headline number is quoted on, through the entry bench.py times: pcr_render_frames, 1 M
+    points, 1024^2, 32 frames per launch, default style (mean_mode AUTO = the reference's sequential float32 mean).
+    40 frames = one full batch + a ragged one, the second prepared by the look-ahead on a side stream; the same frames
+    again after pcr_prefetch_frames, and through the host-buffer entry.  Keys bit-exact against the oracle fed the
+    centres numpy computes (orc.standardize_point_cloud is the reference verbatim — NOT the device's own stats)."""
+    n, W, H, F, B = 1_000_000, 1024, 1024, 40, 32
+    cfg = PRESETS["traj_ball"].for_trajectory(100)
+    traj = synthetic.trajectory(F, n, 3, seed=4)
+    cam_idx = [(37 * f) % 100 for f in range(F)]                       # far, middle and nearest cameras of the schedule
+    cams = [cfg.camera(i, 100, W, H) for i in cam_idx]
+    style = cfg.style()
+    assert style.mean_mode == _native.MEAN_AUTO
+    c = _native.Context(device=0, max_points=n, max_w=W, max_h=H, max_batch=B)
+    try:
+        d = dev(traj)
+        rgba, vis = c.render_frames(d, cams, style, want_vis=True)
+        assert c.counters()["overflow_frames"] == 0
+        sc = orc_scene(orc, cfg)
+        for f in (0, 17, 31, 32, 39):
+            p = orc.transform_coordinates(orc.standardize_point_cloud(traj[f]), cfg.flip_x)      # numpy, reference arithmetic
+            pos4 = np.concatenate([p, np.full((n, 1), cfg.radius, np.float32)], axis=1)
+            want = orc.visibility(pos4, orc_frame(orc, cfg, cam_idx[f], 100, W, H), sc)
+            bad = np.argwhere(keys(vis[f]) != want)
+            assert len(bad) == 0, f"frame {f}: {len(bad)} pixels differ, first {bad[:3].tolist()}"
+            if f in (0, 39):
+                check_image(rgba[f].cpu().numpy(), orc.shade(want, pos4, orc.compute_color(p, mode=0), orc_frame(orc, cfg, cam_idx[f], 100, W, H), sc))
+        # hints change when K0 runs, never what it computes
+        c.prefetch_frames(d[:B], style)
+        c.prefetch_frames(d[B:], style)
+        rgba2, vis2 = c.render_frames(d[:B], cams[:B], style, want_vis=True)
+        rgba3, vis3 = c.render_frames(d[B:], cams[B:], style, want_vis=True)
+        assert torch.equal(vis2, vis[:B]) and torch.equal(rgba2, rgba[:B]) and torch.equal(vis3, vis[B:]) and torch.equal(rgba3, rgba[B:])
+        c.prefetch_frames(d[:B], style)                                  # an unconsumed hint, then dropped
+        c.prefetch_frames(d[:0], style)
+        host_vis = torch.empty((F, H, W), dtype=torch.int64).pin_memory()
+        host_rgba = c.render_frames_host(torch.from_numpy(traj).pin_memory(), cams, style, out_vis=host_vis)
+        assert torch.equal(host_vis, vis.cpu()) and torch.equal(host_rgba, rgba.cpu())
+        # the f64 mean is a different (more accurate) centre: some keys legitimately differ at this size — which is
+        # why the default must be the reference's arithmetic
+        vis64 = c.render_frames(d[:1], cams[:1], cfg.style(mean_mode=_native.MEAN_F64), want_vis=True)[1]
+        p64 = orc.transform_coordinates(orc.standardize_point_cloud(traj[0], exact_mean=True), cfg.flip_x)
+        want64 = orc.visibility(np.concatenate([p64, np.full((n, 1), cfg.radius, np.float32)], axis=1), orc_frame(orc, cfg, cam_idx[0], 100, W, H), sc)
+        np.testing.assert_array_equal(keys(vis64[0]), want64)
+    finally:
+        c.close()
+
+
+def test_c5_film_ten_million_points_through_render_shard(lib, orc):
+    """C5's film (4096^2) at 10 M points through the point-sharded entries on one device: two shards of 5 M points,
+    pcr_stats_partial -> pcr_finalize_stats -> pcr_render_shard -> pcr_zmin merge, keys bit-exact against the oracle on
+    the whole cloud (standardised with the shard totals folded in rank order: the f64 mean of the point-sharded path);
+    the merged buffer also goes through pcr_zmerge_nccl on a one-rank communicator (the NCCL call path of C1)."""
+    from pointcloud_render_b200 import sharding
+    n, W, H, world = 10_000_000, 4096, 4096, 2
+    cfg = PRESETS["example"]
+    x = synthetic.cloud(n, "gauss", 31)
+    style, cam = cfg.style(), cfg.camera(0, 1, W, H)
+    shards = [sharding.point_shard(n, r, world) for r in range(world)]
+    c = _native.Context(device=0, max_points=shards[0][1] - shards[0][0], max_w=W, max_h=H, max_batch=1)
+    try:
+        d = dev(x)
+        parts = torch.stack([c.stats_partial(d[a:b]) for a, b in shards]).contiguous()
+        stats = c.finalize_stats(parts, n)
+        merged = None
+        for a, b in shards:
+            v = c.render_shard(d[a:b], stats, cam, style, id_base=a).clone()
+            merged = v if merged is None else c.zmin_(merged, v)
+        assert c.counters()["overflow_frames"] == 0
+        p = orc.transform_coordinates(orc.standardize_point_cloud(x, exact_mean=True), True)
+        pos4 = np.concatenate([p, np.full((n, 1), cfg.radius, np.float32)], axis=1)
+        want = orc.visibility(pos4, orc_frame(orc, cfg, 0, 1, W, H), orc_scene(orc, cfg))
+        bad = np.argwhere(keys(merged) != want)
+        assert len(bad) == 0, f"{len(bad)} pixels differ, first {bad[:3].tolist()}"
+        comm = sharding.NcclComm(0, 1)
+        try:
+            again = merged.clone()
+            c.zmerge_nccl_(again, comm)
+            torch.cuda.synchronize()
+            assert torch.equal(again, merged)
+        finally:
+            comm.close()
+    finally:
+        c.close()
 
 
 @pytest.mark.parametrize("step", [2, 16, 64])
@@ -686,9 +772,9 @@ def test_work_saving_devices_never_change_a_result(lib, orc, switch, monkeypatch
     for (rgba_on, vis_on), (rgba_off, vis_off) in zip(*outs):
         np.testing.assert_array_equal(vis_on, vis_off)
         np.testing.assert_array_equal(rgba_on, rgba_off)
-    # the dense case against the oracle (f64 mean above 131072 points)
+    # the dense case against the oracle fed the REFERENCE's numpy standardisation
     traj = synthetic.trajectory(3, 300_000, 3, seed=11)
-    p = orc.transform_coordinates(orc.standardize_point_cloud(traj[2], exact_mean=True), cfg.flip_x)
+    p = orc.transform_coordinates(orc.standardize_point_cloud(traj[2]), cfg.flip_x)
     pos4 = np.concatenate([p, np.full((len(p), 1), cfg.radius, np.float32)], axis=1)
     want = orc.visibility(pos4, orc_frame(orc, cfg, 99, 100, 800, 608), orc_scene(orc, cfg))
     np.testing.assert_array_equal(outs[0][0][1][2], want)

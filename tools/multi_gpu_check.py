@@ -6,7 +6,9 @@
 1. frame-sharded trajectory (no collective): every rank renders its block of frames; gathered on
    rank 0 they are byte-identical to rank 0 rendering the whole trajectory alone.
 2. point-sharded cloud (C0 all-gather of shard totals + C1 int64-min all-reduce of the z-buffer +
-   owner-only shading + byte MAX): identical to the single-GPU render, keys and image.
+   owner-only shading + byte MAX): identical to the single-GPU render, keys and image; the same with C1
+   through the C entry pcr_zmerge_nccl (ncclAllReduce(ncclUint64, ncclMin) on our own communicator).
+3. the fused merge over peer memory: identical again.
 Prints one JSON line on rank 0; exits non-zero on any mismatch."""
 import json
 import os
@@ -59,6 +61,14 @@ def main():
     ctx = _native.Context(device=local, max_points=n, max_w=W, max_h=H, max_batch=1)
     vis, rgba = sharding.render_point_sharded(ctx, torch.from_numpy(cloud[a:b]).to(dev), a, n, cam, style)
     torch.cuda.synchronize()
+    # C1 through the C entry: pcr_zmerge_nccl = ncclAllReduce(ncclUint64, ncclMin) on a communicator of our own
+    comm = sharding.NcclComm.from_process_group()
+    vis_c, rgba_c = sharding.render_point_sharded(ctx, torch.from_numpy(cloud[a:b]).to(dev), a, n, cam, style, nccl_comm=comm)
+    torch.cuda.synchronize()
+    same = torch.tensor([int(torch.equal(vis_c, vis) and torch.equal(rgba_c, rgba))], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    report["zmerge_nccl_identical"] = bool(same.item())
+    comm.close()
     if rank == 0:
         whole = torch.from_numpy(cloud).to(dev)
         # same global stats as the sharded run: totals folded in rank order
@@ -102,7 +112,7 @@ def main():
         print(json.dumps(report), flush=True)
         ok = report["frames_identical"] and report["points_keys_identical"] and report["points_image_identical"] \
             and report["two_step_keys_identical"] and report["two_step_image_max_abs_diff"] <= 1 \
-            and report["fused_image_identical"] and report["fused_keys_identical"]
+            and report["fused_image_identical"] and report["fused_keys_identical"] and report["zmerge_nccl_identical"]
         dist.destroy_process_group()
         sys.exit(0 if ok else 1)
     dist.destroy_process_group()
