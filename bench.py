@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with events in the timed region")
+    ap.add_argument("--profile-one-step", action="store_true",
+                    help="for ncu --profile-from-start off: warm up, then ONE device-resident step between cudaProfilerStart/Stop, no timing")
     return ap.parse_args()
 
 
@@ -578,7 +580,7 @@ def main():
     mean_mode = _native.MEAN_F64 if args.mean == "f64" else _native.MEAN_AUTO
     style = cfg.style(color_mode=spec["color_mode"], trails=args.trails and spec["cols"] == 6, mean_mode=mean_mode)
     rgba = torch.empty((B, H, W, 4), dtype=torch.uint8, device="cuda")
-    host_rgba = torch.empty((B, H, W, 4), dtype=torch.uint8).pin_memory()
+    host_rgba = [torch.empty((B, H, W, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
     slots = ring // B
     lookahead = 0 if args.no_lookahead else min(2, slots - 1)
 
@@ -591,9 +593,15 @@ def main():
             ctx.prefetch_frames(resident[ka:ka + B], style)
         ctx.render_frames(resident[k:k + B], cams if cams is not None else cams_all[k:k + B], style, radius=radius, out_rgba=rgba)
 
+    inflight = []
+
     def step_host(s):
+        # the asynchronous form of the host-buffer entry, two calls in flight (the output buffers alternate): the end of
+        # call s (its last kernels, the serial mean's latency, the last D2H copy) overlaps the input copy of call s + 1
         k = (s % slots) * B
-        ctx.render_frames_host(host[k:k + B], cams_all[k:k + B], style, radius_host=radius_np, out_rgba=host_rgba)
+        if len(inflight) >= 2:
+            ctx.host_wait(inflight.pop(0))
+        inflight.append(ctx.render_frames_host_submit(host[k:k + B], cams_all[k:k + B], style, radius_host=radius_np, out_rgba=host_rgba[s % 2])[0])
 
     def barrier():
         torch.cuda.synchronize()
@@ -624,6 +632,14 @@ def main():
     for s in range(args.warmup):
         step_device(s)
     barrier()
+    if args.profile_one_step:
+        torch.cuda.profiler.start()
+        step_device(args.warmup)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profiled": "one device-resident step", "workload": args.workload, "frames": B}), flush=True)
+        ctx.close()
+        return
     ctx.profile_read()
     if not args.no_profile:
         ctx.profile(True)
@@ -655,10 +671,12 @@ def main():
     if not args.no_e2e:
         for s in range(max(args.warmup, 1)):
             step_host(s)
+        ctx.host_wait(-1); inflight.clear()
         barrier()
         t0 = time.perf_counter()
         for s in range(args.steps):
             step_host(args.warmup + s)
+        ctx.host_wait(-1); inflight.clear()                  # every image of every step is in host memory
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         # context for the end-to-end number: what a bare pinned H2D copy of one step's input achieves on this box
@@ -683,7 +701,8 @@ def main():
                "h2d_copy_bound_frames_per_s": sum(h2d_all) * 1e9 / spec["input_bytes_per_frame"],
                "h2d_bytes_per_step": int(B * spec["input_bytes_per_frame"] + (n * 4 if spec["radii"] else 0)),
                "d2h_bytes_per_step": int(B * W * H * 4), "ms_per_step": e2e_s / args.steps * 1e3,
-               "api": "pcr_render_frames_host (pinned host trajectory in, pinned host RGBA8 out; copies overlap kernels)"}
+               "api": "pcr_render_frames_host_submit / pcr_host_wait (pinned host trajectory in, pinned host RGBA8 out; copies overlap "
+                      "kernels; two calls in flight, every step's H2D and D2H inside the timed region)"}
     if sampler:
         sampler.end()           # the clock record covers both timed regions (device-resident and end-to-end)
         sampler.stop()

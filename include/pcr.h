@@ -246,6 +246,17 @@ int pcr_render_frames_host(pcr_ctx* ctx, const void* h_in, int in_is_f64, int64_
                            const pcr_camera* cams, const pcr_style* style,
                            uint64_t* h_vis, uint8_t* h_rgba);
 
+/* The same, asynchronously: submit enqueues the call's copies and kernels and returns a ticket; pcr_host_wait blocks
+ * until that call's images (and keys) are in the caller's buffers (ticket < 0: every call submitted so far).  Two calls
+ * in flight keep the H2D stream busy across calls: the kernels, the serial mean and the D2H copy of the end of call k
+ * overlap the input copy of call k+1 (Mitsuba's write_bitmap is asynchronous in the same way, example_renderer.py:161).
+ * h_in / h_rgba / h_vis / cams' frames must stay valid and untouched until the ticket has been waited for. */
+int pcr_render_frames_host_submit(pcr_ctx* ctx, const void* h_in, int in_is_f64, int64_t n, int cols,
+                                  int n_frames, const float* h_radius, const float* h_rgb,
+                                  const pcr_camera* cams, const pcr_style* style,
+                                  uint64_t* h_vis, uint8_t* h_rgba, int64_t* ticket);
+int pcr_host_wait(pcr_ctx* ctx, int64_t ticket);
+
 /* d_dst[i] = min(d_dst[i], d_src[i]) on uint64 keys — the local half of a z-buffer merge. */
 int pcr_zmin(pcr_ctx* ctx, uint64_t* d_dst, const uint64_t* d_src, int64_t n_px, void* stream);
 

@@ -27,6 +27,7 @@ SYMBOLS = (
     "pcr_set_droplet_mesh", "pcr_droplet_transforms", "pcr_history_trails", "pcr_render_droplet_frames",
     "pcr_peer_alloc", "pcr_ipc_export", "pcr_ipc_open", "pcr_ipc_close", "pcr_peer_set", "pcr_peer_begin_frame",
     "pcr_render_shard_peer", "pcr_shade_shard_peer", "pcr_selftest_scale_div", "pcr_render_transformed", "pcr_prefetch_frames",
+    "pcr_render_frames_host_submit", "pcr_host_wait",
 )
 HISTORY_FRAMES, MAX_CTRL = 20, 21                   # PCR_HISTORY_FRAMES, PCR_MAX_CTRL
 TRAILS_NONE, TRAILS_VELOCITY, TRAILS_HISTORY = 0, 1, 2
@@ -85,6 +86,8 @@ def load_library():
     L.pcr_shade.argtypes = [vp, vp, vp, vp, i64, u32, i32, camp, styp, vp, vp]
     L.pcr_render_transformed.argtypes = [vp, vp, i64, i32, vp, vp, camp, styp, vp, vp, vp]
     L.pcr_render_frames.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, camp, styp, vp, vp, vp]
+    L.pcr_render_frames_host_submit.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, camp, styp, vp, vp, ctypes.POINTER(i64)]
+    L.pcr_host_wait.argtypes = [vp, i64]
     L.pcr_prefetch_frames.argtypes = [vp, vp, i32, i64, i32, i32, styp, vp]
     L.pcr_render_frames_host.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, camp, styp, vp, vp]
     L.pcr_zmin.argtypes = [vp, vp, vp, i64, vp]
@@ -414,20 +417,42 @@ class Context:
         """Host-buffer entry (what a reference script would call): traj_host is a CPU tensor or
         numpy array (F,N,3|6), ideally pinned; returns rgba as a CPU tensor (F,H,W,4).  Synchronous."""
         import torch
+        t = torch.as_tensor(traj_host)
+        ticket, rgba = self.render_frames_host_submit(t, cams, style, radius_host, rgb_host, out_rgba, out_vis)
+        self.host_wait(ticket)
+        self.host_wait(-1)
+        return rgba
+
+    def render_frames_host_submit(self, traj_host, cams, style, radius_host=None, rgb_host=None, out_rgba=None, out_vis=None):
+        """Asynchronous host-buffer entry (pcr_render_frames_host_submit): enqueues the copies and kernels and returns
+        (ticket, rgba); the images are in `rgba` once host_wait(ticket) has returned.  The buffers (and this call's
+        arguments) are kept alive until then."""
+        import torch
         t = _check_points(torch.as_tensor(traj_host), cuda=False, dims=3, what="traj_host")
         F, n, cols = t.shape
         if len(cams) != F:
             raise ValueError("one camera per frame")
         radius_host = None if radius_host is None else _check_vector(torch.as_tensor(radius_host), n, cuda=False, what="radius_host")
         rgb_host = None if rgb_host is None else _check_vector(torch.as_tensor(rgb_host), 3 * n, cuda=False, what="rgb_host")
-        W, H = cams[0].width, cams[0].height
-        cam_arr = (Camera * F)(*cams)
+        W, H = (cams[0].width, cams[0].height) if F else (0, 0)
+        cam_arr = (Camera * max(F, 1))(*cams)
         rgba = out_rgba if out_rgba is not None else torch.empty((F, H, W, 4), dtype=torch.uint8).pin_memory()
         hp = lambda x: None if x is None else ctypes.c_void_p(torch.as_tensor(x).data_ptr())
-        self._check(self.lib.pcr_render_frames_host(self.handle, hp(t), int(t.dtype == torch.float64), n, cols, F,
-                                                    hp(radius_host), hp(rgb_host), cam_arr, ctypes.byref(style),
-                                                    hp(out_vis), hp(rgba)))
-        return rgba
+        ticket = ctypes.c_int64(-1)
+        self._check(self.lib.pcr_render_frames_host_submit(self.handle, hp(t), int(t.dtype == torch.float64), n, cols, F,
+                                                           hp(radius_host), hp(rgb_host), cam_arr, ctypes.byref(style),
+                                                           hp(out_vis), hp(rgba), ctypes.byref(ticket)))
+        if not hasattr(self, "_inflight"):
+            self._inflight = {}
+        self._inflight[int(ticket.value)] = (t, radius_host, rgb_host, rgba, out_vis, cam_arr, style)
+        return int(ticket.value), rgba
+
+    def host_wait(self, ticket=-1):
+        """Block until the host-buffer call `ticket` (or, with -1, every submitted call) has delivered its images."""
+        self._check(self.lib.pcr_host_wait(self.handle, int(ticket)))
+        keep = getattr(self, "_inflight", {})
+        for k in [k for k in keep if ticket < 0 or k <= ticket]:
+            del keep[k]
 
     # ---- droplet scene (traj_renderer.py / traj_vel_renderer.py) ---------------------------
     def set_droplet_mesh(self, verts, n_rings, n_segments):

@@ -21,12 +21,14 @@ using namespace pcr;
 
 namespace {
 
-constexpr int RING_SLOTS = 4;
+constexpr int RING_SLOTS = 16;         // pinned camera-frame ring: the host may run this many uploads ahead of the device
 constexpr int MAX_STAT_BLOCKS = 1184;   // 148 SMs x 8
 // K0 products (standardisation statistics + the compact pre-pass sample) of up to PREP_SLOTS batches can exist ahead of
 // the batch being rendered; region PREP_SLOTS of the stats scratch belongs to the entries that run K0 in line on the
 // caller's stream (pcr_standardize, pcr_stats_partial, pcr_render_transformed, the droplet path).
 constexpr int PREP_SLOTS = 4;
+constexpr int HOST_STAGES = 4;          // staging slots of the host-buffer entry (chunks in flight: H2D | K0 + serial mean | kernels | D2H)
+constexpr int HOST_TICKETS = 16;
 constexpr int INLINE_REGION = PREP_SLOTS;
 
 enum KernelId { KID_STATS = 0, KID_TRANSFORM, KID_PROJECT, KID_SCAN, KID_SCATTER, KID_RASTER, KID_HIZ, KID_SHADE,
@@ -101,11 +103,14 @@ struct pcr_ctx {
 
     // host-buffer pipeline (pcr_render_frames_host), lazily created
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
-    cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
-    void* stage_in[2] = {nullptr, nullptr};
-    uint8_t* stage_rgba[2] = {nullptr, nullptr};
-    uint64_t* stage_vis[2] = {nullptr, nullptr};
+    cudaEvent_t ev_h2d[HOST_STAGES] = {}, ev_comp[HOST_STAGES] = {}, ev_d2h[HOST_STAGES] = {};
+    void* stage_in[HOST_STAGES] = {};
+    uint8_t* stage_rgba[HOST_STAGES] = {};
+    uint64_t* stage_vis[HOST_STAGES] = {};      // allocated when a caller first asks for the keys
     size_t stage_in_bytes = 0;
+    unsigned long long host_chunks = 0;         // chunks submitted so far, over all calls (chunk c uses slot c % HOST_STAGES)
+    cudaEvent_t ticket_ev[HOST_TICKETS] = {};
+    long long tickets = 0;                      // calls submitted so far
     float *stage_radius = nullptr, *stage_rgb = nullptr;
 
     long long last_overflow_frames = 0;
@@ -341,10 +346,10 @@ int launch_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, long long n, int
     // the reference's own (sequential, input-dtype) mean replaces the f64 one unless the caller asked for PCR_MEAN_F64
     const bool sequential = finalize == 1 && mean_mode != PCR_MEAN_F64;
     if (sequential) {
-        if (in_is_f64)
-            LAUNCH(KID_MEAN, stream, k_mean_sequential<double><<<nb, 128, 0, stream>>>((const double*)d_in, n, cols, frame_stride, stats));
-        else
-            LAUNCH(KID_MEAN, stream, k_mean_sequential<float><<<nb, 128, 0, stream>>>((const float*)d_in, n, cols, frame_stride, stats));
+#define PCR_MEAN(T, C) LAUNCH(KID_MEAN, stream, (k_mean_sequential<T, C><<<nb, 32, 0, stream>>>((const T*)d_in, n, frame_stride, stats)))
+        if (in_is_f64) { if (cols == 3) PCR_MEAN(double, 3); else PCR_MEAN(double, 6); }
+        else { if (cols == 3) PCR_MEAN(float, 3); else PCR_MEAN(float, 6); }
+#undef PCR_MEAN
     }
     return PCR_OK;
 }
@@ -761,17 +766,18 @@ void pcr_destroy(pcr_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     void* frees[] = {ctx->surv_count, ctx->ext, ctx->sph, ctx->rect, ctx->partials, ctx->stats, ctx->done, ctx->counts, ctx->offsets,
-                     ctx->cursor, ctx->p_sph, ctx->p_ci, ctx->p_ext, ctx->tile_state, ctx->sample, ctx->scan_part, ctx->scan_ready, ctx->fill_list, ctx->fill_count, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_in[0], ctx->stage_in[1],
-                     ctx->stage_rgba[0], ctx->stage_rgba[1], ctx->stage_vis[0], ctx->stage_vis[1], ctx->stage_radius, ctx->stage_rgb,
+                     ctx->cursor, ctx->p_sph, ctx->p_ci, ctx->p_ext, ctx->tile_state, ctx->sample, ctx->scan_part, ctx->scan_ready, ctx->fill_list, ctx->fill_count, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_radius, ctx->stage_rgb,
                      ctx->peer_merged, ctx->peer_image, ctx->mesh_verts, ctx->mesh_prof, ctx->plan, ctx->dstats, ctx->dxf, ctx->dctrl, ctx->dcount};
     for (void* p : frees) if (p) cudaFree(p);
     if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
     for (int k = 0; k < RING_SLOTS; ++k) if (ctx->ring_ev[k]) cudaEventDestroy(ctx->ring_ev[k]);
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < HOST_STAGES; ++k) {
         if (ctx->ev_h2d[k]) cudaEventDestroy(ctx->ev_h2d[k]);
         if (ctx->ev_comp[k]) cudaEventDestroy(ctx->ev_comp[k]);
         if (ctx->ev_d2h[k]) cudaEventDestroy(ctx->ev_d2h[k]);
+        for (void* q : {(void*)ctx->stage_in[k], (void*)ctx->stage_rgba[k], (void*)ctx->stage_vis[k]}) if (q) cudaFree(q);
     }
+    for (cudaEvent_t ev : ctx->ticket_ev) if (ev) cudaEventDestroy(ev);
     for (ProfRec& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     for (pcr_ctx::PrepSlot& p : ctx->prep) {
@@ -1076,15 +1082,15 @@ int pcr_prefetch_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n
     return PCR_OK;
 }
 
-int pcr_render_frames_host(pcr_ctx* ctx, const void* h_in, int in_is_f64, int64_t n, int cols, int n_frames, const float* h_radius,
-                           const float* h_rgb, const pcr_camera* cams, const pcr_style* style, uint64_t* h_vis, uint8_t* h_rgba)
+int pcr_render_frames_host_submit(pcr_ctx* ctx, const void* h_in, int in_is_f64, int64_t n, int cols, int n_frames, const float* h_radius,
+                                  const float* h_rgb, const pcr_camera* cams, const pcr_style* style, uint64_t* h_vis, uint8_t* h_rgba,
+                                  int64_t* ticket)
 {
     int rc = check_common(ctx, n, cols, style);
     if (rc) return rc;
     if (n_frames < 0 || !cams || !h_rgba || !h_in || n < 1) return fail(ctx, PCR_ERR_INVALID, "pcr_render_frames_host: NULL buffer or n < 1");
-    if (n_frames == 0) return PCR_OK;
     CK(cudaSetDevice(ctx->device));
-    const int W = cams[0].width, H = cams[0].height;
+    const int W = n_frames ? cams[0].width : 1, H = n_frames ? cams[0].height : 1;
     if (W > ctx->max_w || H > ctx->max_h) return fail(ctx, PCR_ERR_CAPACITY, "frame larger than the context");
     const size_t px = (size_t)W * H, elem = in_is_f64 ? 8 : 4;
     const size_t frame_bytes = (size_t)n * cols * elem;
@@ -1093,53 +1099,59 @@ int pcr_render_frames_host(pcr_ctx* ctx, const void* h_in, int in_is_f64, int64_
         CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < HOST_STAGES; ++k) {
             CK(cudaEventCreateWithFlags(&ctx->ev_h2d[k], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&ctx->ev_comp[k], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&ctx->ev_d2h[k], cudaEventDisableTiming));
             CK(cudaMalloc((void**)&ctx->stage_rgba[k], (size_t)B * ctx->max_w * ctx->max_h * 4));
-            CK(cudaMalloc((void**)&ctx->stage_vis[k], (size_t)B * ctx->max_w * ctx->max_h * 8));
         }
+        for (int k = 0; k < HOST_TICKETS; ++k) CK(cudaEventCreateWithFlags(&ctx->ticket_ev[k], cudaEventDisableTiming));
         CK(cudaMalloc((void**)&ctx->stage_radius, sizeof(float) * ctx->max_points));
         CK(cudaMalloc((void**)&ctx->stage_rgb, sizeof(float) * 3 * ctx->max_points));
     }
+    if (h_vis && !ctx->stage_vis[0]) {
+        CK(cudaDeviceSynchronize());
+        for (int k = 0; k < HOST_STAGES; ++k) CK(cudaMalloc((void**)&ctx->stage_vis[k], (size_t)B * ctx->max_w * ctx->max_h * 8));
+    }
     if (ctx->stage_in_bytes < (size_t)B * frame_bytes) {
         CK(cudaDeviceSynchronize());
-        for (int k = 0; k < 2; ++k) {
+        for (pcr_ctx::PrepSlot& p : ctx->prep) p.valid = false;          // hints on the old staging buffers are void
+        for (int k = 0; k < HOST_STAGES; ++k) {
             if (ctx->stage_in[k]) CK(cudaFree(ctx->stage_in[k]));
             ctx->stage_in[k] = nullptr;
             CK(cudaMalloc(&ctx->stage_in[k], (size_t)B * frame_bytes));
         }
         ctx->stage_in_bytes = (size_t)B * frame_bytes;
     }
-    // earlier stream-ordered calls may still be using the scratch and the staging buffers
-    if ((rc = enter(ctx, ctx->s_h2d))) return rc;
+    // Work that OTHER entry points left on a caller's stream may still be using the scratch: the kernels wait for it.
+    // (Earlier host-buffer calls are ordered by the staging slots' own events — the copies of this call overlap the
+    // kernels of the previous one.)
     if ((rc = enter(ctx, ctx->s_comp))) return rc;
     const float *d_radius = nullptr, *d_rgb = nullptr;
     if (h_radius) { CK(cudaMemcpyAsync(ctx->stage_radius, h_radius, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->s_comp)); d_radius = ctx->stage_radius; }
     if (h_rgb) { CK(cudaMemcpyAsync(ctx->stage_rgb, h_rgb, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->s_comp)); d_rgb = ctx->stage_rgb; }
-    // chunks of at most B frames, but at least ~8 chunks per call so that the H2D copy of chunk
-    // k+1, the kernels of chunk k and the D2H copy of chunk k-1 overlap even for short calls
-    // The call's time is the H2D stream's (it is busy from the first byte to the last) plus what is left to do after
-    // the last input chunk has arrived — its kernels and its D2H copy.  So the tail of the call is cut into ever
-    // smaller chunks (C, ..., C, C/2, C/4, ..., 1).
+    // Chunks of at most B frames, but at least ~8 chunks per call so that the H2D copy of chunk k+1, the K0 (+ serial
+    // mean) of chunk k, the kernels of chunk k-1 and the D2H copy of chunk k-2 overlap even for short calls.  The call's
+    // time is the H2D stream's (busy from the first byte to the last) plus what is left to do after the last input chunk
+    // has arrived, so the tail of the call is cut into ever smaller chunks (C, ..., C, C/2, C/4, ..., 1).
     const int C = std::max(1, std::min(B, (n_frames + 7) / 8));
-    int chunk = 0;
-    for (int f0 = 0, nb = 0; f0 < n_frames; f0 += nb, ++chunk) {
+    for (int f0 = 0, nb = 0; f0 < n_frames; f0 += nb) {
         const int left = n_frames - f0;
         nb = left > C ? C : std::max(1, left / 2);
-        const int k = chunk & 1;
-        if (chunk >= 2) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[k], 0));   // input slot free again
+        const unsigned long long chunk = ctx->host_chunks++;
+        const int k = (int)(chunk % HOST_STAGES);
+        const bool reused = chunk >= (unsigned long long)HOST_STAGES;
+        if (reused) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[k], 0));       // input slot free again
         CK(cudaMemcpyAsync(ctx->stage_in[k], (const char*)h_in + (size_t)f0 * frame_bytes, (size_t)nb * frame_bytes,
                            cudaMemcpyHostToDevice, ctx->s_h2d));
         CK(cudaEventRecord(ctx->ev_h2d[k], ctx->s_h2d));
         // K0 (+ the serial reference-exact mean) of this chunk starts the moment its bytes have landed, on a side
-        // stream: it overlaps the previous chunk's kernels instead of delaying this chunk's
+        // stream: it overlaps the previous chunks' kernels instead of delaying this chunk's
         if ((rc = pcr_prefetch_frames(ctx, ctx->stage_in[k], in_is_f64, n, cols, nb, style, ctx->s_h2d))) return rc;
         CK(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_h2d[k], 0));
-        if (chunk >= 2) CK(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_d2h[k], 0));  // output slot drained
+        if (reused) CK(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_d2h[k], 0));      // output slot drained
         rc = pcr_render_frames(ctx, ctx->stage_in[k], in_is_f64, n, cols, nb, d_radius, d_rgb, cams + f0, style,
-                               ctx->stage_vis[k], ctx->stage_rgba[k], ctx->s_comp);
+                               h_vis ? ctx->stage_vis[k] : nullptr, ctx->stage_rgba[k], ctx->s_comp);
         if (rc) return rc;
         CK(cudaEventRecord(ctx->ev_comp[k], ctx->s_comp));
         CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_comp[k], 0));
@@ -1147,9 +1159,34 @@ int pcr_render_frames_host(pcr_ctx* ctx, const void* h_in, int in_is_f64, int64_
         if (h_vis) CK(cudaMemcpyAsync(h_vis + (size_t)f0 * px, ctx->stage_vis[k], (size_t)nb * px * 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
         CK(cudaEventRecord(ctx->ev_d2h[k], ctx->s_d2h));
     }
-    CK(cudaStreamSynchronize(ctx->s_d2h));
-    CK(cudaStreamSynchronize(ctx->s_comp));
+    const long long t = ctx->tickets++;
+    CK(cudaEventRecord(ctx->ticket_ev[t % HOST_TICKETS], ctx->s_d2h));
+    if (ticket) *ticket = t;
     return PCR_OK;
+}
+
+int pcr_host_wait(pcr_ctx* ctx, int64_t ticket)
+{
+    if (!ctx) return PCR_ERR_INVALID;
+    if (!ctx->s_d2h || ctx->tickets == 0) return PCR_OK;
+    CK(cudaSetDevice(ctx->device));
+    if (ticket < 0 || ticket >= ctx->tickets) {              // everything submitted so far
+        CK(cudaStreamSynchronize(ctx->s_d2h));
+        CK(cudaStreamSynchronize(ctx->s_comp));
+        return PCR_OK;
+    }
+    // a ticket older than the ring has been overwritten by a later call's event: waiting for that is conservative
+    CK(cudaEventSynchronize(ctx->ticket_ev[ticket % HOST_TICKETS]));
+    return PCR_OK;
+}
+
+int pcr_render_frames_host(pcr_ctx* ctx, const void* h_in, int in_is_f64, int64_t n, int cols, int n_frames, const float* h_radius,
+                           const float* h_rgb, const pcr_camera* cams, const pcr_style* style, uint64_t* h_vis, uint8_t* h_rgba)
+{
+    int64_t ticket = -1;
+    int rc = pcr_render_frames_host_submit(ctx, h_in, in_is_f64, n, cols, n_frames, h_radius, h_rgb, cams, style, h_vis, h_rgba, &ticket);
+    if (rc) return rc;
+    return pcr_host_wait(ctx, -1);
 }
 
 int pcr_zmin(pcr_ctx* ctx, uint64_t* d_dst, const uint64_t* d_src, int64_t n_px, void* stream)

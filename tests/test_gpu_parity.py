@@ -250,8 +250,14 @@ def test_capacity_and_argument_errors(ctx):
     big = torch.zeros(((1 << 20) + 1, 3), device="cuda")
     with pytest.raises(RuntimeError, match="max_points"):
         ctx.standardize(big, cfg.style())
-    with pytest.raises(RuntimeError, match="cols"):
+    with pytest.raises(ValueError, match="shape"):                      # the wrapper refuses it ...
         ctx.standardize(torch.zeros((8, 4), device="cuda"), cfg.style())
+    import ctypes                                                       # ... and so does the C entry behind it
+    z, st = torch.zeros((8, 4), device="cuda"), cfg.style()
+    out = torch.zeros((8, 4), device="cuda")
+    rc = ctx.lib.pcr_standardize(ctx.handle, ctypes.c_void_p(z.data_ptr()), 0, 8, 4, None, None, ctypes.byref(st),
+                                 ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(out.data_ptr()), None, None, None)
+    assert rc == -1 and b"cols" in ctx.lib.pcr_last_error(ctx.handle)
     cam = _native.make_camera((1, 1, 1), (1, 1, 1), width=64, height=64)
     with pytest.raises(RuntimeError, match="degenerate camera"):
         ctx.render(torch.zeros((4, 4), device="cuda"), torch.zeros((4, 4), device="cuda"), cam, cfg.style())
@@ -722,6 +728,28 @@ def test_wrappers_reject_wrong_dtype_layout_and_device(ctx):
         ctx.stats_partial(torch.zeros((100, 4), dtype=torch.float32, device="cuda"))
     with pytest.raises(ValueError):
         ctx.render_shard(six, torch.zeros(9, dtype=torch.float64, device="cuda"), cam, style)
+
+
+def test_host_entry_asynchronous_calls_in_flight(ctx, orc):
+    """pcr_render_frames_host_submit / pcr_host_wait: three calls submitted back to back (more chunks than staging
+    slots, so slots, prepared-stats slots and camera ring are all recycled while earlier chunks are still in flight)
+    deliver exactly what the synchronous entry and the device entry deliver."""
+    F, n, W, H = 11, 20_000, 400, 304
+    cfg = PRESETS["traj_ball"].for_trajectory(100)
+    style = cfg.style()
+    calls = []
+    for c in range(3):
+        traj = synthetic.trajectory(F, n, 3, seed=40 + c)
+        cams = [cfg.camera((9 * f + c) % 100, 100, W, H) for f in range(F)]
+        calls.append((traj, cams, torch.from_numpy(traj).pin_memory(), torch.empty((F, H, W), dtype=torch.int64).pin_memory()))
+    tickets = [ctx.render_frames_host_submit(host, cams, style, out_vis=hv) for _, cams, host, hv in calls]
+    ctx.host_wait(tickets[1][0])
+    ctx.host_wait(-1)
+    for (traj, cams, host, hv), (_, rgba) in zip(calls, tickets):
+        want_rgba, want_vis = ctx.render_frames(dev(traj), cams, style, want_vis=True)
+        assert torch.equal(hv, want_vis.cpu()) and torch.equal(rgba, want_rgba.cpu())
+        sync = ctx.render_frames_host(host, cams, style)
+        assert torch.equal(sync, rgba)
 
 
 def test_zero_frames_and_tiny_inputs(ctx):
