@@ -51,6 +51,7 @@ def parse_args():
                     help="C5 on several GPUs: z-merge fused into the raster over peer memory (default) or NCCL min all-reduce")
     ap.add_argument("--mean", default="auto", choices=["auto", "f64"],
                     help="standardisation centre: auto = the reference's sequential np.mean (default), f64 = parallel float64 sums")
+    ap.add_argument("--lookahead", type=int, default=4, help="steps of K0 look-ahead (the serial mean's latency is ~3 steps at H)")
     ap.add_argument("--no-lookahead", action="store_true", help="do not hint the next steps' frames (pcr_prefetch_frames)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -91,10 +92,10 @@ def config_dict(name, spec, ring, n_gpus, trails=False, mean="auto"):
 
 
 def ring_frames(spec, requested=0):
-    """Resident frames per GPU: a multiple of frames_per_step, at least 4 steps (so that the whole camera schedule is
-    visited and a two-step look-ahead never meets the slice being rendered) whose inputs exceed the 126 MB L2."""
+    """Resident frames per GPU: a multiple of frames_per_step, at least 5 steps (so that the whole camera schedule is
+    visited and a four-step look-ahead never meets the slice being rendered) whose inputs exceed the 126 MB L2."""
     B = spec["frames_per_step"]
-    ring = requested or max(4 * B, B * int(np.ceil(160e6 / spec["input_bytes_per_frame"] / B)))
+    ring = requested or max(5 * B, B * int(np.ceil(160e6 / spec["input_bytes_per_frame"] / B)))
     return (ring + B - 1) // B * B
 
 
@@ -582,7 +583,7 @@ def main():
     rgba = torch.empty((B, H, W, 4), dtype=torch.uint8, device="cuda")
     host_rgba = [torch.empty((B, H, W, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
     slots = ring // B
-    lookahead = 0 if args.no_lookahead else min(2, slots - 1)
+    lookahead = 0 if args.no_lookahead else min(args.lookahead, slots - 1)
 
     def step_device(s, cams=None):
         # K0 of step s + lookahead (statistics incl. the serial reference-exact mean, pre-pass sample) is started now

@@ -232,7 +232,7 @@ int pcr_render_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, 
  * overlap whatever renders in the meantime (the reference does the same on the host: traj_renderer.py:718-743
  * standardises every frame before it renders the first).  pcr_render_frames looks its batches up (by address and
  * shape, max_batch frames at a time) and computes only what nobody prepared; results never depend on hints.  At
- * most 4 batches are kept (further frames are simply not prefetched; an unconsumed hint is dropped when its slot is
+ * most 6 batches are kept (further frames are simply not prefetched; an unconsumed hint is dropped when its slot is
  * needed).  n_frames == 0 drops every hint.  The caller must not modify hinted frames before rendering them. */
 int pcr_prefetch_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, int cols, int n_frames,
                         const pcr_style* style, void* stream);

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpcr.so")
+LIB_PATH = os.environ.get("PCR_LIBPCR") or os.path.join(_HERE, "libpcr.so")      # PCR_LIBPCR: a diagnostics build (A/B runs)
 
 ID_FLOOR = 0xFFFFFFFE
 ID_MISS = 0xFFFFFFFF

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libpcr.so")
+LIB = os.environ.get("PCR_LIB_OUT") or os.path.join(HERE, "libpcr.so")           # PCR_LIB_OUT: where a diagnostics build goes
 SOURCES = [os.path.join(CSRC, "pcr_api.cu")]
 DEPS = SOURCES + [os.path.join(CSRC, "pcr_kernels.cuh"), os.path.join(CSRC, "pcr_droplets.cuh"), os.path.join(ROOT, "include", "pcr.h")]
 

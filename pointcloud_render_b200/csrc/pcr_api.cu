@@ -26,7 +26,7 @@ constexpr int MAX_STAT_BLOCKS = 1184;   // 148 SMs x 8
 // K0 products (standardisation statistics + the compact pre-pass sample) of up to PREP_SLOTS batches can exist ahead of
 // the batch being rendered; region PREP_SLOTS of the stats scratch belongs to the entries that run K0 in line on the
 // caller's stream (pcr_standardize, pcr_stats_partial, pcr_render_transformed, the droplet path).
-constexpr int PREP_SLOTS = 4;
+constexpr int PREP_SLOTS = 6;
 constexpr int HOST_STAGES = 4;          // staging slots of the host-buffer entry (chunks in flight: H2D | K0 + serial mean | kernels | D2H)
 constexpr int HOST_TICKETS = 16;
 constexpr int INLINE_REGION = PREP_SLOTS;
@@ -1130,11 +1130,13 @@ int pcr_render_frames_host_submit(pcr_ctx* ctx, const void* h_in, int in_is_f64,
     const float *d_radius = nullptr, *d_rgb = nullptr;
     if (h_radius) { CK(cudaMemcpyAsync(ctx->stage_radius, h_radius, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->s_comp)); d_radius = ctx->stage_radius; }
     if (h_rgb) { CK(cudaMemcpyAsync(ctx->stage_rgb, h_rgb, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->s_comp)); d_rgb = ctx->stage_rgb; }
-    // Chunks of at most B frames, but at least ~8 chunks per call so that the H2D copy of chunk k+1, the K0 (+ serial
+    // Chunks of at most B frames, but at least ~4 chunks per call so that the H2D copy of chunk k+1, the K0 (+ serial
     // mean) of chunk k, the kernels of chunk k-1 and the D2H copy of chunk k-2 overlap even for short calls.  The call's
     // time is the H2D stream's (busy from the first byte to the last) plus what is left to do after the last input chunk
     // has arrived, so the tail of the call is cut into ever smaller chunks (C, ..., C, C/2, C/4, ..., 1).
-    const int C = std::max(1, std::min(B, (n_frames + 7) / 8));
+    // (a quarter of the call per chunk: with HOST_STAGES chunks in flight the whole call's serial means run side by side —
+    // their latency, ~3 ms per million points, is the same for one frame or thirty-two)
+    const int C = std::max(1, std::min(B, (n_frames + 3) / 4));
     for (int f0 = 0, nb = 0; f0 < n_frames; f0 += nb) {
         const int left = n_frames - f0;
         nb = left > C ? C : std::max(1, left / 2);

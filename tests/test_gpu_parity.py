@@ -302,7 +302,8 @@ def test_point_sharded_merge_equals_unsharded(ctx, orc):
     n, W, H, k = 200_000, 1024, 1024, 4
     cfg = PRESETS["example"]
     x = synthetic.cloud(n, "gauss", 1)
-    cam, style = cfg.camera(0, 1, W, H), cfg.style(color_mode=1)
+    # (the point-sharded entries take the parallel float64 mean: a float32 fold cannot be split across shards)
+    cam, style = cfg.camera(0, 1, W, H), cfg.style(color_mode=1, mean_mode=_native.MEAN_F64)
     pos4, attr4, stats = ctx.standardize(dev(x), style, want_stats=True)
     vis_full, rgba_full = ctx.render(pos4, attr4, cam, style)
     merged, parts = None, []
