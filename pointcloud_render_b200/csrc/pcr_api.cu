@@ -94,6 +94,14 @@ struct pcr_ctx {
     int two_phase = 1;                // K2a's coarse-then-fine Hi-Z cull (PCR_TWO_PHASE=0 disables: diagnostics)
     int occlusion_step = 16;          // the pre-pass rasterises every step-th point
     long long occlusion_min_points = 1 << 17;
+    // Two nested pre-passes for large clouds (n >= occlusion_min_points2): every (step2 * ratio)-th point first, then every
+    // step2-th point culled by the first one's Hi-Z, then all points culled by the second one's — the occluders
+    // themselves are mostly buried, and the coarser level removes them before they cost a list entry.
+    int occlusion_levels = 1;         // 1: the single pre-pass (default); 2 (PCR_OCCLUSION_LEVELS=2): the two nested ones — measured on H
+                                      // they halve the main pass's pairs but cost as much as they save (20.3 k vs 21.2 k frames/s)
+    int occlusion_step2 = 8, occlusion_ratio = 8;
+    long long occlusion_min_points2 = 1 << 19;
+    unsigned int* hz_b = nullptr;     // second Hi-Z buffer (the finer pre-pass builds its own while it is culled by the coarser one's)
     uint64_t* vis = nullptr;          // lazily allocated when the caller passes d_vis == NULL
     FrameDev* d_frames = nullptr;
     FrameDev* h_frames = nullptr;     // pinned ring: RING_SLOTS x max_batch
@@ -357,6 +365,12 @@ int launch_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, long long n, int
 double* inline_stats(pcr_ctx* ctx) { return ctx->stats + (size_t)INLINE_REGION * ctx->max_batch * 10; }
 double* slot_stats(pcr_ctx* ctx, int slot) { return ctx->stats + (size_t)slot * ctx->max_batch * 10; }
 
+// two nested occluder pre-passes (pcr_ctx::occlusion_levels) for this cloud size?
+bool two_prepasses(const pcr_ctx* ctx, long long n)
+{
+    return ctx->occlusion_levels >= 2 && n >= ctx->occlusion_min_points2 && n > (long long)ctx->occlusion_step2 * ctx->occlusion_ratio * 64;
+}
+
 // ---- prepared batches (see pcr_ctx::PrepSlot) ----------------------------------------------------------------------
 // What the occluder pre-pass needs from K0 for frames of n points: every sstep-th point, compact.
 struct SamplePlan { bool sampled; int sstep; long long stride; };          // stride in elements per frame
@@ -364,7 +378,7 @@ SamplePlan sample_plan(const pcr_ctx* ctx, long long n)
 {
     const bool occl = ctx->occlusion > 0 || (ctx->occlusion < 0 && n >= ctx->occlusion_min_points);
     SamplePlan sp;
-    sp.sstep = ctx->occlusion_step;
+    sp.sstep = two_prepasses(ctx, n) ? ctx->occlusion_step2 : ctx->occlusion_step;
     sp.sampled = ctx->sample_prepass && occl && n > sp.sstep;
     sp.stride = sp.sampled ? ((n + sp.sstep - 1) / sp.sstep) * 3 : 0;
     return sp;
@@ -534,7 +548,7 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
     const long long slots = 2 * ctx->max_points;       // survivor slots per frame: sphere + trail per point
 
     // one binning + raster pass over `np` spheres (sphere i = point i*step)
-    auto pass = [&](long long np, int step, const unsigned int* hz, int seeded, int do_trails, const PeerDev& peer, unsigned int* hz_out) -> int {
+    auto pass = [&](long long np, int step, const unsigned int* hz, int seeded, int do_trails, const PeerDev& peer, unsigned int* hz_out, int sample_step) -> int {
         unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((np + 2047) / 2048, std::max(1, 2 * resident / nb)));
         // (films too large for the shared-memory histograms use per-pair global atomics; the same large chunks serve them
         // best — 2048-point chunks made 24 k tiny blocks of a 50 M-point cloud: K2a / K2b 435 / 454 -> 379 / 390 us on C5)
@@ -550,7 +564,8 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
             // the pre-pass reads the compact sample K0 wrote (point i of the pass = sample row i) when there is one
             RawSrc rsrc = raw ? *raw : RawSrc{};
             int fetch_step = step;
-            if (raw && step > 1 && raw->sample) { rsrc.in = raw->sample; rsrc.frame_stride = raw->sample_stride; rsrc.cols = 3; fetch_step = 1; }
+            // (the sample holds every sample_step-th point; a coarser pass strides over it)
+            if (raw && step > 1 && raw->sample && step % sample_step == 0) { rsrc.in = raw->sample; rsrc.frame_stride = raw->sample_stride; rsrc.cols = 3; fetch_step = step / sample_step; }
             const RawSrc* rawp = raw ? &rsrc : nullptr;
 #define PCR_PROJECT(T, RAWB, TRB, posarg, strarg, rawarg)                                                                        \
     LAUNCH(KID_PROJECT, stream, (k_project_count<T, RAWB, TRB><<<grid, BIN_THREADS, sm, stream>>>(                               \
@@ -601,21 +616,40 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
     };
 
     const bool occl = ctx->occlusion > 0 || (ctx->occlusion < 0 && n >= ctx->occlusion_min_points);
-    if (occl && n > ctx->occlusion_step) {
+    const int hzn2 = (((W + HZ_W - 1) / HZ_W + 3) / 4) * (((H + HZ_H - 1) / HZ_H + 3) / 4);
+    // Hi-Z of a finished pre-pass: level-1 entries were written by k_fill_tiles (empty tiles), the scan (untouched tiles, lazy
+    // fill) and the raster (single-item tiles); the tiles split into several items are re-read, then level 2 is built
+    auto finish_hiz = [&](unsigned int* hzbuf, int listed) -> int {
+        dim3 grid((unsigned)(listed ? std::min((tiles + 7) / 8, 8) : (tiles + 7) / 8), nb);
+        LAUNCH(KID_HIZ, stream, k_hiz_split<<<grid, 256, 0, stream>>>(ctx->d_frames, bin, v, vis_stride, hzbuf, ctx->hz_cap, listed));
+        dim3 grid2((unsigned)((hzn2 + 255) / 256), nb);
+        LAUNCH(KID_HIZ, stream, k_hiz2<<<grid2, 256, 0, stream>>>(ctx->d_frames, hzbuf, ctx->hz_cap));
+        return PCR_OK;
+    };
+    if (occl && two_prepasses(ctx, n)) {
+        // every (step2 * ratio)-th point -> Hi-Z A; every step2-th point, culled by A and seeded with the first pass's keys
+        // -> Hi-Z B (which starts as a copy of A: tiles the second pass does not touch keep their entries); then all points
+        const int s1 = ctx->occlusion_step2, s0 = s1 * ctx->occlusion_ratio;
+        if (!ctx->hz_b) CK(cudaMalloc((void**)&ctx->hz_b, sizeof(unsigned int) * (size_t)ctx->max_batch * (size_t)ctx->hz_cap));
+        int rc = pass((n + s0 - 1) / s0, s0, nullptr, 0, 0, no_peer, ctx->hz, s1);
+        if (rc) return rc;
+        if ((rc = finish_hiz(ctx->hz, lazy ? 1 : 0))) return rc;
+        CK(cudaMemcpyAsync(ctx->hz_b, ctx->hz, sizeof(unsigned int) * (size_t)nb * (size_t)ctx->hz_cap, cudaMemcpyDeviceToDevice, stream));
+        rc = pass((n + s1 - 1) / s1, s1, ctx->hz, 1, 0, no_peer, ctx->hz_b, s1);
+        if (rc) return rc;
+        if ((rc = finish_hiz(ctx->hz_b, 0))) return rc;             // (the seeded scan's list holds other tiles: look at every tile)
+        rc = pass(n, 1, ctx->hz_b, 1, trails, peer_final, nullptr, s1);
+        if (rc) return rc;
+    } else if (occl && n > ctx->occlusion_step) {
         // occluder pre-pass (every step-th point, true ids) -> Hi-Z -> main pass seeded with its keys
         const int step = ctx->occlusion_step;
-        int rc = pass((n + step - 1) / step, step, nullptr, 0, 0, no_peer, ctx->hz);       // trails are never occluders; only the final pass pushes
+        int rc = pass((n + step - 1) / step, step, nullptr, 0, 0, no_peer, ctx->hz, step);       // trails are never occluders; only the final pass pushes
         if (rc) return rc;
-        // level-1 Hi-Z entries were written by k_fill_tiles (empty tiles) and the raster (single-item tiles)
-        dim3 grid((unsigned)(lazy ? std::min((tiles + 7) / 8, 8) : (tiles + 7) / 8), nb);
-        LAUNCH(KID_HIZ, stream, k_hiz_split<<<grid, 256, 0, stream>>>(ctx->d_frames, bin, v, vis_stride, ctx->hz, ctx->hz_cap, lazy ? 1 : 0));
-        const int hzn2 = (((W + HZ_W - 1) / HZ_W + 3) / 4) * (((H + HZ_H - 1) / HZ_H + 3) / 4);
-        dim3 grid2((unsigned)((hzn2 + 255) / 256), nb);
-        LAUNCH(KID_HIZ, stream, k_hiz2<<<grid2, 256, 0, stream>>>(ctx->d_frames, ctx->hz, ctx->hz_cap));
-        rc = pass(n, 1, ctx->hz, 1, trails, peer_final, nullptr);
+        if ((rc = finish_hiz(ctx->hz, lazy ? 1 : 0))) return rc;
+        rc = pass(n, 1, ctx->hz, 1, trails, peer_final, nullptr, step);
         if (rc) return rc;
     } else {
-        int rc = pass(n, 1, nullptr, 0, trails, peer_final, nullptr);
+        int rc = pass(n, 1, nullptr, 0, trails, peer_final, nullptr, 1);
         if (rc) return rc;
     }
     if (rgba) return launch_shade(ctx, st, vis, vis_stride, pos, attr, in_stride, raw, n, nb, id_base, owner_only, W, H, rgba, rgba_stride, stream,
@@ -694,6 +728,9 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     if (const char* e = getenv("PCR_STATS_AHEAD")) ctx->stats_ahead = atoi(e);
     if (const char* e = getenv("PCR_SCATTER_THREADS")) ctx->scatter_threads = std::min(BIN_THREADS, std::max(32, atoi(e) & ~31));
     if (const char* e = getenv("PCR_OCCLUSION_STEP")) ctx->occlusion_step = std::max(2, atoi(e));
+    if (const char* e = getenv("PCR_OCCLUSION_LEVELS")) ctx->occlusion_levels = atoi(e);
+    if (const char* e = getenv("PCR_OCCLUSION_STEP2")) ctx->occlusion_step2 = std::max(2, atoi(e));
+    if (const char* e = getenv("PCR_OCCLUSION_RATIO")) ctx->occlusion_ratio = std::max(2, atoi(e));
     const size_t B = (size_t)max_batch, N = (size_t)max_points, Tn = (size_t)ctx->tiles_cap;
     cudaError_t e = cudaSetDevice(device);
     cudaDeviceProp prop;
@@ -766,7 +803,7 @@ void pcr_destroy(pcr_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     void* frees[] = {ctx->surv_count, ctx->ext, ctx->sph, ctx->rect, ctx->partials, ctx->stats, ctx->done, ctx->counts, ctx->offsets,
-                     ctx->cursor, ctx->p_sph, ctx->p_ci, ctx->p_ext, ctx->tile_state, ctx->sample, ctx->scan_part, ctx->scan_ready, ctx->fill_list, ctx->fill_count, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_radius, ctx->stage_rgb,
+                     ctx->cursor, ctx->p_sph, ctx->p_ci, ctx->p_ext, ctx->tile_state, ctx->sample, ctx->scan_part, ctx->scan_ready, ctx->fill_list, ctx->fill_count, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->hz_b, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_radius, ctx->stage_rgb,
                      ctx->peer_merged, ctx->peer_image, ctx->mesh_verts, ctx->mesh_prof, ctx->plan, ctx->dstats, ctx->dxf, ctx->dctrl, ctx->dcount};
     for (void* p : frees) if (p) cudaFree(p);
     if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
@@ -1279,7 +1316,7 @@ int pcr_set_occlusion(pcr_ctx* ctx, int mode, int step, int64_t min_points)
     if (!ctx) return PCR_ERR_INVALID;
     if (mode < -1 || mode > 1 || (step != 0 && step < 2)) return fail(ctx, PCR_ERR_INVALID, "pcr_set_occlusion: mode in {-1,0,1}, step >= 2");
     ctx->occlusion = mode;
-    if (step) ctx->occlusion_step = step;
+    if (step) { ctx->occlusion_step = step; ctx->occlusion_step2 = std::max(2, step / 2); }
     if (min_points > 0) ctx->occlusion_min_points = min_points;
     return PCR_OK;
 }
