@@ -27,7 +27,7 @@ constexpr int MAX_STAT_BLOCKS = 1184;   // 148 SMs x 8
 // the batch being rendered; region PREP_SLOTS of the stats scratch belongs to the entries that run K0 in line on the
 // caller's stream (pcr_standardize, pcr_stats_partial, pcr_render_transformed, the droplet path).
 constexpr int PREP_SLOTS = 6;
-constexpr int HOST_STAGES = 4;          // staging slots of the host-buffer entry (chunks in flight: H2D | K0 + serial mean | kernels | D2H)
+constexpr int HOST_STAGES = 6;          // staging slots of the host-buffer entry (chunks in flight: H2D | K0 + serial mean | kernels | D2H)
 constexpr int HOST_TICKETS = 16;
 constexpr int INLINE_REGION = PREP_SLOTS;
 
@@ -117,6 +117,10 @@ struct pcr_ctx {
     uint64_t* stage_vis[HOST_STAGES] = {};      // allocated when a caller first asks for the keys
     size_t stage_in_bytes = 0;
     unsigned long long host_chunks = 0;         // chunks submitted so far, over all calls (chunk c uses slot c % HOST_STAGES)
+    // PCR_HOST_TRACE=1 (diagnostics): timed events at the stages of every chunk of the host pipeline, printed by pcr_host_wait(-1)
+    int host_trace = 0;
+    struct TraceRec { unsigned long long chunk; int nb; cudaEvent_t h2d0, h2d1, ready, comp0, comp1, d2h1; };
+    std::vector<TraceRec> trace;
     cudaEvent_t ticket_ev[HOST_TICKETS] = {};
     long long tickets = 0;                      // calls submitted so far
     float *stage_radius = nullptr, *stage_rgb = nullptr;
@@ -354,7 +358,10 @@ int launch_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, long long n, int
     // the reference's own (sequential, input-dtype) mean replaces the f64 one unless the caller asked for PCR_MEAN_F64
     const bool sequential = finalize == 1 && mean_mode != PCR_MEAN_F64;
     if (sequential) {
-#define PCR_MEAN(T, C) LAUNCH(KID_MEAN, stream, (k_mean_sequential<T, C><<<nb, 32, 0, stream>>>((const T*)d_in, n, frame_stride, stats)))
+        // one warp per frame, MEAN_FRAMES_PER_BLOCK frames per block; the dynamic shared memory request keeps a block alone on its SM
+        const int mean_blocks = (nb + MEAN_FRAMES_PER_BLOCK - 1) / MEAN_FRAMES_PER_BLOCK;
+        const size_t mean_smem = MEAN_SMEM_PER_FRAME * MEAN_FRAMES_PER_BLOCK;
+#define PCR_MEAN(T, C) LAUNCH(KID_MEAN, stream, (k_mean_sequential<T, C><<<mean_blocks, 32 * MEAN_FRAMES_PER_BLOCK, mean_smem, stream>>>((const T*)d_in, n, frame_stride, stats, nb)))
         if (in_is_f64) { if (cols == 3) PCR_MEAN(double, 3); else PCR_MEAN(double, 6); }
         else { if (cols == 3) PCR_MEAN(float, 3); else PCR_MEAN(float, 6); }
 #undef PCR_MEAN
@@ -729,6 +736,7 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     if (const char* e = getenv("PCR_SCATTER_THREADS")) ctx->scatter_threads = std::min(BIN_THREADS, std::max(32, atoi(e) & ~31));
     if (const char* e = getenv("PCR_OCCLUSION_STEP")) ctx->occlusion_step = std::max(2, atoi(e));
     if (const char* e = getenv("PCR_OCCLUSION_LEVELS")) ctx->occlusion_levels = atoi(e);
+    if (const char* e = getenv("PCR_HOST_TRACE")) ctx->host_trace = atoi(e);
     if (const char* e = getenv("PCR_OCCLUSION_STEP2")) ctx->occlusion_step2 = std::max(2, atoi(e));
     if (const char* e = getenv("PCR_OCCLUSION_RATIO")) ctx->occlusion_ratio = std::max(2, atoi(e));
     const size_t B = (size_t)max_batch, N = (size_t)max_points, Tn = (size_t)ctx->tiles_cap;
@@ -743,6 +751,13 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<float, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<double, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<double, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+        {
+            const int mean_smem = (int)(MEAN_SMEM_PER_FRAME * MEAN_FRAMES_PER_BLOCK);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mean_sequential<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mean_smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mean_sequential<float, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, mean_smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mean_sequential<double, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mean_smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mean_sequential<double, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, mean_smem);
+        }
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_raster_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(RasterStage<false>) * RASTER_STAGES));
@@ -1168,35 +1183,50 @@ int pcr_render_frames_host_submit(pcr_ctx* ctx, const void* h_in, int in_is_f64,
     if (h_radius) { CK(cudaMemcpyAsync(ctx->stage_radius, h_radius, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->s_comp)); d_radius = ctx->stage_radius; }
     if (h_rgb) { CK(cudaMemcpyAsync(ctx->stage_rgb, h_rgb, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->s_comp)); d_rgb = ctx->stage_rgb; }
     // Chunks of at most B frames, but at least ~4 chunks per call so that the H2D copy of chunk k+1, the K0 (+ serial
-    // mean) of chunk k, the kernels of chunk k-1 and the D2H copy of chunk k-2 overlap even for short calls.  The call's
-    // time is the H2D stream's (busy from the first byte to the last) plus what is left to do after the last input chunk
-    // has arrived, so the tail of the call is cut into ever smaller chunks (C, ..., C, C/2, C/4, ..., 1).
-    // (a quarter of the call per chunk: with HOST_STAGES chunks in flight the whole call's serial means run side by side —
-    // their latency, ~3 ms per million points, is the same for one frame or thirty-two)
-    const int C = std::max(1, std::min(B, (n_frames + 3) / 4));
+    // mean) of chunk k, the kernels of chunk k-1 and the D2H copy of chunk k-2 overlap even for short calls.
+    // With the parallel float64 mean a chunk's work is proportional to its size, so the tail of the call is cut into ever
+    // smaller chunks (C, ..., C, C/2, C/4, ..., 1): what is left to do after the last byte has arrived shrinks with it.
+    // With the reference's serial mean every chunk carries the same ~3-4 ms of latency however small it is (measured:
+    // PCR_HOST_TRACE=1) and small chunks only use up staging slots: equal chunks, a quarter of the call each.
+    const bool serial_mean = style->mean_mode != PCR_MEAN_F64;
+    int C = std::max(1, std::min(B, (n_frames + 3) / 4));
+    if (serial_mean) C = std::min(C, 8);            // (PREP_SLOTS chunks of 8 frames in flight outrun the H2D copy by far)
     for (int f0 = 0, nb = 0; f0 < n_frames; f0 += nb) {
         const int left = n_frames - f0;
-        nb = left > C ? C : std::max(1, left / 2);
+        nb = serial_mean ? std::min(C, left) : (left > C ? C : std::max(1, left / 2));
         const unsigned long long chunk = ctx->host_chunks++;
         const int k = (int)(chunk % HOST_STAGES);
         const bool reused = chunk >= (unsigned long long)HOST_STAGES;
         if (reused) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[k], 0));       // input slot free again
+        pcr_ctx::TraceRec tr = {chunk, nb, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        if (ctx->host_trace) {
+            for (cudaEvent_t* ev : {&tr.h2d0, &tr.h2d1, &tr.ready, &tr.comp0, &tr.comp1, &tr.d2h1}) CK(cudaEventCreate(ev));
+            CK(cudaEventRecord(tr.h2d0, ctx->s_h2d));
+        }
         CK(cudaMemcpyAsync(ctx->stage_in[k], (const char*)h_in + (size_t)f0 * frame_bytes, (size_t)nb * frame_bytes,
                            cudaMemcpyHostToDevice, ctx->s_h2d));
         CK(cudaEventRecord(ctx->ev_h2d[k], ctx->s_h2d));
+        if (ctx->host_trace) CK(cudaEventRecord(tr.h2d1, ctx->s_h2d));
         // K0 (+ the serial reference-exact mean) of this chunk starts the moment its bytes have landed, on a side
         // stream: it overlaps the previous chunks' kernels instead of delaying this chunk's
         if ((rc = pcr_prefetch_frames(ctx, ctx->stage_in[k], in_is_f64, n, cols, nb, style, ctx->s_h2d))) return rc;
         CK(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_h2d[k], 0));
         if (reused) CK(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_d2h[k], 0));      // output slot drained
+        if (ctx->host_trace) {
+            // (the prepared slot's ready event, seen from its own stream, and the start of this chunk's kernels)
+            for (pcr_ctx::PrepSlot& p : ctx->prep) if (p.valid && p.in == ctx->stage_in[k]) CK(cudaEventRecord(tr.ready, p.stream ? p.stream : ctx->s_comp));
+            CK(cudaEventRecord(tr.comp0, ctx->s_comp));
+        }
         rc = pcr_render_frames(ctx, ctx->stage_in[k], in_is_f64, n, cols, nb, d_radius, d_rgb, cams + f0, style,
                                h_vis ? ctx->stage_vis[k] : nullptr, ctx->stage_rgba[k], ctx->s_comp);
         if (rc) return rc;
         CK(cudaEventRecord(ctx->ev_comp[k], ctx->s_comp));
+        if (ctx->host_trace) CK(cudaEventRecord(tr.comp1, ctx->s_comp));
         CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_comp[k], 0));
         CK(cudaMemcpyAsync(h_rgba + (size_t)f0 * px * 4, ctx->stage_rgba[k], (size_t)nb * px * 4, cudaMemcpyDeviceToHost, ctx->s_d2h));
         if (h_vis) CK(cudaMemcpyAsync(h_vis + (size_t)f0 * px, ctx->stage_vis[k], (size_t)nb * px * 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
         CK(cudaEventRecord(ctx->ev_d2h[k], ctx->s_d2h));
+        if (ctx->host_trace) { CK(cudaEventRecord(tr.d2h1, ctx->s_d2h)); ctx->trace.push_back(tr); }
     }
     const long long t = ctx->tickets++;
     CK(cudaEventRecord(ctx->ticket_ev[t % HOST_TICKETS], ctx->s_d2h));
@@ -1212,6 +1242,23 @@ int pcr_host_wait(pcr_ctx* ctx, int64_t ticket)
     if (ticket < 0 || ticket >= ctx->tickets) {              // everything submitted so far
         CK(cudaStreamSynchronize(ctx->s_d2h));
         CK(cudaStreamSynchronize(ctx->s_comp));
+        if (ctx->host_trace && !ctx->trace.empty()) {
+            cudaDeviceSynchronize();
+            const cudaEvent_t t0 = ctx->trace.front().h2d0;
+            fprintf(stderr, "[pcr host trace] chunk frames | h2d start end | stats+mean ready | kernels start end | d2h end   (ms)\n");
+            for (pcr_ctx::TraceRec& r : ctx->trace) {
+                float a = 0, b = 0, c = -1, d = 0, e = 0, f = 0;
+                cudaEventElapsedTime(&a, t0, r.h2d0); cudaEventElapsedTime(&b, t0, r.h2d1);
+                if (cudaEventQuery(r.ready) == cudaSuccess) cudaEventElapsedTime(&c, t0, r.ready);
+                cudaGetLastError();
+                cudaEventElapsedTime(&d, t0, r.comp0); cudaEventElapsedTime(&e, t0, r.comp1); cudaEventElapsedTime(&f, t0, r.d2h1);
+                fprintf(stderr, "[pcr host trace] %5llu %3d | %8.3f %8.3f | %8.3f | %8.3f %8.3f | %8.3f\n", r.chunk, r.nb, a, b, c, d, e, f);
+            }
+            for (pcr_ctx::TraceRec& r : ctx->trace)
+                for (cudaEvent_t ev : {r.h2d0, r.h2d1, r.ready, r.comp0, r.comp1, r.d2h1}) if (ev && ev != t0) cudaEventDestroy(ev);
+            cudaEventDestroy(t0);
+            ctx->trace.clear();
+        }
         return PCR_OK;
     }
     // a ticket older than the ring has been overwritten by a later call's event: waiting for that is conservative
