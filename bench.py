@@ -121,28 +121,91 @@ def cameras_for(spec, ring, rank=0):
 
 # --------------------------------------------------------------------------------------------------
 # host placement
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if part:
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def smi_topology():
+    """`nvidia-smi topo -m` (text) and, per GPU index, the CPU / NUMA affinity columns it prints — the only place the
+    GPU's socket shows up when the container hides /sys/bus/pci/devices/*/numa_node (it reads -1 there)."""
+    import re
+    try:
+        text = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+    except (OSError, subprocess.TimeoutExpired):
+        return "", {}
+    text = re.sub(r"\x1b\[[0-9;]*m", "", text)
+    aff = {}
+    for line in text.splitlines():
+        m = re.match(r"^GPU(\d+)\s", line)
+        if not m:
+            continue
+        toks = line.split()
+        lists = [t for t in toks[1:] if re.fullmatch(r"\d+(-\d+)?(,\d+(-\d+)?)*", t)]
+        # after the link matrix: CPU affinity (a range list), NUMA affinity, GPU NUMA id
+        cpu = next((t for t in lists if "-" in t or "," in t), None)
+        rest = lists[lists.index(cpu) + 1:] if cpu in lists else []
+        aff[int(m.group(1))] = {"cpu_affinity": cpu, "numa_affinity": rest[0] if rest else None}
+    return text, aff
+
+
 def bind_to_gpu_numa(local_rank):
-    """Run this rank (and first-touch its pinned staging memory) on the NUMA node its GPU hangs off, when
-    the container lets us see that.  Pure placement: returns a small dict for the JSON line."""
+    """Run this rank (and first-touch its pinned staging memory: cudaHostAlloc pages are touched by the calling thread)
+    on the NUMA node its GPU hangs off.  The node comes from sysfs, or — when the container reports -1 there — from the
+    CPU-affinity column of `nvidia-smi topo -m`.  Pure placement: returns a small dict for the JSON line."""
     info = {"bound": False}
     try:
         import torch
         p = torch.cuda.get_device_properties(local_rank)
         bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
-        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        node = -1
+        try:
+            node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        except OSError:
+            pass
         info.update(pci=bdf, numa_node=node)
-        if node < 0:
-            return info
-        cpus = set()
-        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
+        cpus, source = set(), None
+        if node >= 0:
+            cpus, source = _parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read()), "sysfs"
+        else:
+            _, aff = smi_topology()
+            # torch's device index follows CUDA_VISIBLE_DEVICES; nvidia-smi lists physical GPUs: match by PCI bus id
+            idx = local_rank
+            try:
+                q = subprocess.run(["nvidia-smi", "--query-gpu=index,pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True, timeout=20).stdout
+                for line in q.splitlines():
+                    i, bus = [x.strip() for x in line.split(",")]
+                    if bus.lower().endswith(bdf[5:].lower()):
+                        idx = int(i)
+            except (OSError, ValueError, subprocess.TimeoutExpired):
+                pass
+            a = aff.get(idx)
+            if a and a["cpu_affinity"]:
+                cpus, source = _parse_cpulist(a["cpu_affinity"]), "nvidia-smi topo -m"
+                info.update(smi_numa_affinity=a["numa_affinity"], smi_cpu_affinity=a["cpu_affinity"])
+        # memory first: prefer the GPU's node for everything this process allocates from here on (the pinned trajectory
+        # ring and image buffers) — works even when the container's CPU set is not on that node
+        mem_node = node if node >= 0 else (int(info["smi_numa_affinity"]) if str(info.get("smi_numa_affinity", "")).isdigit() else -1)
+        if mem_node >= 0:
+            import ctypes
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = (ctypes.c_ulong * 16)()
+            mask[mem_node // 64] = 1 << (mem_node % 64)
+            MPOL_PREFERRED, SYS_set_mempolicy = 1, 238               # x86_64
+            rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, mask, 16 * 64)
+            info.update(mempolicy=f"preferred node {mem_node}" if rc == 0 else f"set_mempolicy failed (errno {ctypes.get_errno()})")
         allowed = cpus & os.sched_getaffinity(0)
-        if allowed:
+        if allowed and len(allowed) < len(os.sched_getaffinity(0)):
             os.sched_setaffinity(0, allowed)
-            info.update(bound=True, cpus=len(allowed))
+            info.update(bound=True, cpus=len(allowed), source=source)
+        elif allowed:
+            info.update(cpus=len(allowed), source=source, note="the GPU's CPU set is every CPU this process may use: nothing to bind")
     except Exception as e:          # placement is best effort
-        info["note"] = f"{type(e).__name__}: {e}"[:120]
+        info["note"] = f"{type(e).__name__}: {e}"[:160]
     return info
 
 
@@ -785,6 +848,7 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "kernels": kernels, "roofline": roofline,
             "per_schedule_third": thirds,
             "clocks": clocks, "host_placement": numa_all if world > 1 else numa,
+            "nvidia_smi_topo": smi_topology()[0][:4000] if world > 1 else None,
             "pairs_last_frame": counters["pairs_last_frame"], "overflow_frames": counters["overflow_frames"]}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(spec, host_np, radius_np)
