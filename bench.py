@@ -646,7 +646,10 @@ def main():
     rgba = torch.empty((B, H, W, 4), dtype=torch.uint8, device="cuda")
     host_rgba = [torch.empty((B, H, W, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
     slots = ring // B
-    lookahead = 0 if args.no_lookahead else min(args.lookahead, slots - 1)
+    # hinted steps ahead: bounded by the ring and by the library's prepared-batch slots (6, one kept free; a step is
+    # ceil(B / max_batch) batches)
+    batches_per_step = -(-B // ctx.max_batch)
+    lookahead = 0 if args.no_lookahead else max(1, min(args.lookahead, slots - 1, 5 // batches_per_step))
 
     def step_device(s, cams=None):
         # K0 of step s + lookahead (statistics incl. the serial reference-exact mean, pre-pass sample) is started now

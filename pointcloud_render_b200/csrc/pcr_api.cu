@@ -33,12 +33,12 @@ constexpr int INLINE_REGION = PREP_SLOTS;
 
 enum KernelId { KID_STATS = 0, KID_TRANSFORM, KID_PROJECT, KID_SCAN, KID_SCATTER, KID_RASTER, KID_HIZ, KID_SHADE,
                 KID_ZMIN, KID_AXIS, KID_FILL, KID_MEAN, KID_LUT, KID_DROP_PREP, KID_FILL_FLOOR, KID_RASTER_POLY, KID_RASTER_DROP,
-                KID_SHADE_DROP, KID_PEER_INIT, KID_SHADE_PEER, KID_SHADE_FLOOR, KID_COUNT };
+                KID_SHADE_DROP, KID_PEER_INIT, KID_SHADE_PEER, KID_SHADE_FLOOR, KID_TRAILS, KID_COUNT };
 const char* const kKernelNames[KID_COUNT] = {"k_stats", "k_transform", "k_project_count", "k_scan_tiles", "k_scatter",
                                              "k_raster_tiles", "k_hiz", "k_shade", "k_zmin", "k_axis_transform",
                                              "k_fill_tiles", "k_mean_sequential", "k_build_floor_lut", "k_droplet_prepare",
                                              "k_fill_floor", "k_raster_polylines", "k_raster_droplets", "k_shade_droplets", "k_peer_init_rows",
-                                             "k_shade_peer", "k_shade_floor_tiles"};
+                                             "k_shade_peer", "k_shade_floor_tiles", "k_raster_trails"};
 constexpr size_t PROF_MAX_RECORDS = 1 << 16;
 
 struct ProfRec { int kid; cudaEvent_t a, b; };
@@ -145,7 +145,13 @@ struct pcr_ctx {
     size_t dstats_frames = 0;
     float *dxf = nullptr, *dctrl = nullptr;
     int* dcount = nullptr;
-    size_t dprep_points = 0;          // capacity of dxf / dctrl / dcount in points (batch * n)
+    unsigned char* dbin = nullptr;    // depth bin of every droplet (occlusion cull by depth slabs)
+    unsigned int* dhist = nullptr;    // [max_batch][DROP_BINS], zero between batches
+    int* dedges = nullptr;            // [max_batch][DROP_SLABS + 1] first depth bin of every slab
+    int* dstarts = nullptr;           // [max_batch][DROP_SLABS + 1] droplets in front of every slab
+    int* dcursor = nullptr;           // [max_batch][DROP_SLABS]
+    int* dorder = nullptr;            // [batch * n] droplet indices in slab order
+    size_t dprep_points = 0;          // capacity of dxf / dctrl / dcount / dbin in points (batch * n)
 
     // The scratch is shared by every entry point, so work issued on DIFFERENT streams must not
     // overlap: each entry waits for the previous entry's last event when the stream changed.
@@ -545,7 +551,9 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
     if (trails && 2 * (unsigned long long)n > 0xFFFFFFF0ull) return fail(ctx, PCR_ERR_INVALID, "too many points for trail ids (n + i)");
     const uint32_t cap_id_base = trails ? (uint32_t)n : 0u;
     // lazy floor fill: tiles in which nothing is drawn get their keys from K4 — only when K4 follows in this very call
-    const bool lazy = ctx->lazy_fill && rgba != nullptr && push == nullptr;
+    // (trails are merged into the finished keys of every tile with atomicMin: the tiles nothing was binned in need their
+    // floor keys first, so frames with trails take the eager fill)
+    const bool lazy = ctx->lazy_fill && rgba != nullptr && push == nullptr && !trails;
     if (lazy) bin.tile_state = ctx->tile_state;
     if (trails && !ctx->p_ext) {
         CK(cudaMalloc((void**)&ctx->p_ext, sizeof(float4) * (size_t)ctx->max_batch * (size_t)ctx->pair_cap));
@@ -623,6 +631,7 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
     };
 
     const bool occl = ctx->occlusion > 0 || (ctx->occlusion < 0 && n >= ctx->occlusion_min_points);
+    const unsigned int* trail_hz = nullptr;
     const int hzn2 = (((W + HZ_W - 1) / HZ_W + 3) / 4) * (((H + HZ_H - 1) / HZ_H + 3) / 4);
     // Hi-Z of a finished pre-pass: level-1 entries were written by k_fill_tiles (empty tiles), the scan (untouched tiles, lazy
     // fill) and the raster (single-item tiles); the tiles split into several items are re-read, then level 2 is built
@@ -645,7 +654,8 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         rc = pass((n + s1 - 1) / s1, s1, ctx->hz, 1, 0, no_peer, ctx->hz_b, s1);
         if (rc) return rc;
         if ((rc = finish_hiz(ctx->hz_b, 0))) return rc;             // (the seeded scan's list holds other tiles: look at every tile)
-        rc = pass(n, 1, ctx->hz_b, 1, trails, peer_final, nullptr, s1);
+        rc = pass(n, 1, ctx->hz_b, 1, 0, peer_final, nullptr, s1);
+        trail_hz = ctx->hz_b;
         if (rc) return rc;
     } else if (occl && n > ctx->occlusion_step) {
         // occluder pre-pass (every step-th point, true ids) -> Hi-Z -> main pass seeded with its keys
@@ -653,11 +663,21 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         int rc = pass((n + step - 1) / step, step, nullptr, 0, 0, no_peer, ctx->hz, step);       // trails are never occluders; only the final pass pushes
         if (rc) return rc;
         if ((rc = finish_hiz(ctx->hz, lazy ? 1 : 0))) return rc;
-        rc = pass(n, 1, ctx->hz, 1, trails, peer_final, nullptr, step);
+        rc = pass(n, 1, ctx->hz, 1, 0, peer_final, nullptr, step);
+        trail_hz = ctx->hz;
         if (rc) return rc;
     } else {
-        int rc = pass(n, 1, nullptr, 0, trails, peer_final, nullptr, 1);
+        int rc = pass(n, 1, nullptr, 0, 0, peer_final, nullptr, 1);
         if (rc) return rc;
+    }
+    if (trails) {
+        // the velocity trail of every point, as a line raster straight into the finished keys (k_raster_trails); culled by
+        // the occluder pre-pass's Hi-Z where there was one
+        dim3 grid((unsigned)((n + 7) / 8), nb);
+        if (raw->is_f64)
+            LAUNCH(KID_TRAILS, stream, k_raster_trails<double><<<grid, 256, 0, stream>>>(raw_frames<double>(raw), n, st, ctx->d_frames, cap_id_base, v, vis_stride, trail_hz, ctx->hz_cap));
+        else
+            LAUNCH(KID_TRAILS, stream, k_raster_trails<float><<<grid, 256, 0, stream>>>(raw_frames<float>(raw), n, st, ctx->d_frames, cap_id_base, v, vis_stride, trail_hz, ctx->hz_cap));
     }
     if (rgba) return launch_shade(ctx, st, vis, vis_stride, pos, attr, in_stride, raw, n, nb, id_base, owner_only, W, H, rgba, rgba_stride, stream,
                                   lazy ? ctx->tile_state : nullptr);
@@ -819,7 +839,7 @@ void pcr_destroy(pcr_ctx* ctx)
     cudaDeviceSynchronize();
     void* frees[] = {ctx->surv_count, ctx->ext, ctx->sph, ctx->rect, ctx->partials, ctx->stats, ctx->done, ctx->counts, ctx->offsets,
                      ctx->cursor, ctx->p_sph, ctx->p_ci, ctx->p_ext, ctx->tile_state, ctx->sample, ctx->scan_part, ctx->scan_ready, ctx->fill_list, ctx->fill_count, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->hz_b, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_radius, ctx->stage_rgb,
-                     ctx->peer_merged, ctx->peer_image, ctx->mesh_verts, ctx->mesh_prof, ctx->plan, ctx->dstats, ctx->dxf, ctx->dctrl, ctx->dcount};
+                     ctx->peer_merged, ctx->peer_image, ctx->mesh_verts, ctx->mesh_prof, ctx->plan, ctx->dstats, ctx->dxf, ctx->dctrl, ctx->dcount, ctx->dbin, ctx->dhist, ctx->dedges, ctx->dstarts, ctx->dcursor, ctx->dorder};
     for (void* p : frees) if (p) cudaFree(p);
     if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
     for (int k = 0; k < RING_SLOTS; ++k) if (ctx->ring_ev[k]) cudaEventDestroy(ctx->ring_ev[k]);
@@ -1128,6 +1148,9 @@ int pcr_prefetch_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n
         const char* in = (const char*)d_in + (size_t)k * B * (size_t)(n * cols) * elem;
         const int nb = std::min(B, n_frames - k * B);
         if (find_prepared(ctx, in, in_is_f64, n, cols, nb, style->mean_mode, sp) >= 0) continue;
+        int free_slots = 0;
+        for (const pcr_ctx::PrepSlot& p : ctx->prep) free_slots += !p.valid;
+        if (free_slots <= 1) break;                            // a hint never displaces an earlier one (those frames come first), and one slot stays free for un-hinted work
         int slot;
         if ((rc = prepare_batch(ctx, in, in_is_f64, n, cols, nb, style->mean_mode, sp, s, ctx->stats_ahead != 0, &slot))) return rc;
     }
@@ -1321,7 +1344,7 @@ int pcr_counters(pcr_ctx* ctx, int64_t out[4], void* stream)
     {
         unsigned long long dbg[16];
         CK(cudaMemcpy(dbg, ctx->stat_pairs, sizeof(dbg), cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[pcr stats] warp-candidates %llu  cull-iterations %llu  box-pass %llu\n", dbg[8], dbg[9], dbg[10]);
+        fprintf(stderr, "[pcr stats] warp-candidates %llu  cull-iterations %llu  box-pass %llu  droplets tested %llu culled %llu\n", dbg[8], dbg[9], dbg[10], dbg[11], dbg[12]);
         CK(cudaMemset(ctx->stat_pairs + 8, 0, 8 * sizeof(unsigned long long)));
     }
 #endif
@@ -1543,8 +1566,17 @@ int pcr_render_droplet_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int
             ctx->dstats_frames = (size_t)total;
         }
         if (ctx->dprep_points < need_pts) {
-            for (void* p : {(void*)ctx->dxf, (void*)ctx->dctrl, (void*)ctx->dcount}) if (p) CK(cudaFree(p));
-            ctx->dxf = nullptr; ctx->dctrl = nullptr; ctx->dcount = nullptr; ctx->dprep_points = 0;
+            for (void* p : {(void*)ctx->dxf, (void*)ctx->dctrl, (void*)ctx->dcount, (void*)ctx->dbin, (void*)ctx->dorder}) if (p) CK(cudaFree(p));
+            ctx->dxf = nullptr; ctx->dctrl = nullptr; ctx->dcount = nullptr; ctx->dbin = nullptr; ctx->dorder = nullptr; ctx->dprep_points = 0;
+            CK(cudaMalloc((void**)&ctx->dbin, need_pts));
+            CK(cudaMalloc((void**)&ctx->dorder, sizeof(int) * need_pts));
+            if (!ctx->dhist) {
+                CK(cudaMalloc((void**)&ctx->dhist, sizeof(unsigned int) * (size_t)ctx->max_batch * DROP_BINS));
+                CK(cudaMemset(ctx->dhist, 0, sizeof(unsigned int) * (size_t)ctx->max_batch * DROP_BINS));
+                CK(cudaMalloc((void**)&ctx->dedges, sizeof(int) * (size_t)ctx->max_batch * (DROP_SLABS + 1)));
+                CK(cudaMalloc((void**)&ctx->dstarts, sizeof(int) * (size_t)ctx->max_batch * (DROP_SLABS + 1)));
+                CK(cudaMalloc((void**)&ctx->dcursor, sizeof(int) * (size_t)ctx->max_batch * DROP_SLABS));
+            }
             CK(cudaMalloc((void**)&ctx->dxf, sizeof(float) * 12 * need_pts));
             CK(cudaMalloc((void**)&ctx->dctrl, sizeof(float) * 3 * MAX_CTRL * need_pts));
             CK(cudaMalloc((void**)&ctx->dcount, sizeof(int) * need_pts));
@@ -1587,14 +1619,35 @@ int pcr_render_droplet_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int
         }
         dim3 pgrid((unsigned)((W + 63) / 64), (unsigned)((H + 3) / 4), nb);
         LAUNCH(KID_FILL_FLOOR, s, k_fill_floor<<<pgrid, 256, 0, s>>>(ctx->d_frames, st, vis, vis_stride));
+        // dense scenes: depth slabs nearest first, the Hi-Z rebuilt after each (see k_raster_droplets); the trails last,
+        // culled by everything in front of them
+        const bool cull = ctx->occlusion > 0 || (ctx->occlusion < 0 && n >= 16384);
+        const unsigned int* hzp = nullptr;
+        // persistent grids: the warps stride over the (slab's) droplet list
+        const int drop_blocks_sm = std::max(1, std::min(2048 / (32 * drop_warps), (int)((size_t)ctx->smem_optin / std::max<size_t>(smem, 1))));
+        const long long per_pass = cull ? (n + 1) / 2 : n;                                   // the largest slab holds a quarter; leave slack
+        const dim3 dgrid((unsigned)std::max<long long>(1, std::min<long long>((per_pass + drop_warps - 1) / drop_warps, (long long)ctx->num_sms * drop_blocks_sm * 4 / nb + 1)), nb);
+        if (cull) {
+            LAUNCH(KID_DROP_PREP, s, k_droplet_depth_bins<<<dim3((unsigned)((n + 1023) / 1024), nb), 256, 0, s>>>(ctx->d_frames, n, mesh.bound, ctx->dxf, ctx->dbin, ctx->dhist));
+            LAUNCH(KID_DROP_PREP, s, k_droplet_slab_edges<<<nb, 32, 0, s>>>(ctx->dhist, n, ctx->dedges, ctx->dstarts, ctx->dcursor));
+            LAUNCH(KID_DROP_PREP, s, k_droplet_slab_order<<<dim3((unsigned)((n + 1023) / 1024), nb), 256, 0, s>>>(n, ctx->dbin, ctx->dedges, ctx->dcursor, ctx->dorder));
+            const dim3 hgrid((unsigned)((W + 255) / 256), (unsigned)((H + HZ_H - 1) / HZ_H), nb);
+            for (int slab = 0; slab < DROP_SLABS; ++slab) {
+                LAUNCH(KID_RASTER_DROP, s, k_raster_droplets<<<dgrid, 32 * drop_warps, smem, s>>>(ctx->d_frames, n, mesh, 0u, ctx->dxf, vis, vis_stride, ctx->dorder,
+                                                                                                  ctx->dstarts, slab, hzp, ctx->hz_cap, ctx->stat_pairs));
+                if (slab + 1 < DROP_SLABS) {
+                    LAUNCH(KID_HIZ, s, k_hiz_from_vis<<<hgrid, 256, 0, s>>>(ctx->d_frames, vis, vis_stride, ctx->hz, ctx->hz_cap));
+                    hzp = ctx->hz;
+                }
+            }
+        } else {
+            LAUNCH(KID_RASTER_DROP, s, k_raster_droplets<<<dgrid, 32 * drop_warps, smem, s>>>(ctx->d_frames, n, mesh, 0u, ctx->dxf, vis, vis_stride, nullptr, nullptr, 0,
+                                                                                              nullptr, ctx->hz_cap, ctx->stat_pairs));
+        }
         if (st.trails && cols == 6) {
             dim3 grid((unsigned)((n + 7) / 8), nb);
             LAUNCH(KID_RASTER_POLY, s, k_raster_polylines<<<grid, 256, 0, s>>>(ctx->d_frames, n, st.trail_radius, (uint32_t)n, ctx->dctrl,
-                                                                              ctx->dcount, vis, vis_stride));
-        }
-        {
-            dim3 grid((unsigned)((n + drop_warps - 1) / drop_warps), nb);
-            LAUNCH(KID_RASTER_DROP, s, k_raster_droplets<<<grid, 32 * drop_warps, smem, s>>>(ctx->d_frames, n, mesh, 0u, ctx->dxf, vis, vis_stride));
+                                                                              ctx->dcount, vis, vis_stride, hzp, ctx->hz_cap));
         }
         uint32_t* rgba = (uint32_t*)(d_rgba + (size_t)f0 * px * 4);
         if (in_is_f64)

@@ -246,7 +246,8 @@ __device__ __forceinline__ void to_camera(const FrameDev& f, const float* X, flo
 // with atomicMin.  Un-binned on purpose: a trail covers a few dozen pixels.
 __global__ void __launch_bounds__(256)
 k_raster_polylines(const FrameDev* __restrict__ frames, long long n, float radius, uint32_t cap_id_base, const float* __restrict__ ctrl,
-                   const int* __restrict__ count, unsigned long long* __restrict__ vis, long long vis_stride)
+                   const int* __restrict__ count, unsigned long long* __restrict__ vis, long long vis_stride,
+                   const unsigned int* __restrict__ hz, int hz_stride)
 {
     const int b = blockIdx.y;
     const FrameDev& f = frames[b];
@@ -266,6 +267,10 @@ k_raster_polylines(const FrameDev* __restrict__ frames, long long n, float radiu
         { const float X[3] = {__ldg(cp + 3 * s + 3), __ldg(cp + 3 * s + 4), __ldg(cp + 3 * s + 5)}; to_camera(f, X, B); }
         int x0, x1, y0, y1;
         if (!capsule_bbox(f, A, B, radius, x0, x1, y0, y1)) continue;
+        // occlusion cull (see k_raster_droplets): a segment entirely behind the farthest pre-pass winner of every 8x4 pixel
+        // block its box touches cannot win a pixel
+        if (hz && nearest_depth_bits(fminf(A[2], B[2]), radius) > hiz_far_bits_warp(hz + (size_t)b * hz_stride, (f.W + HZ_W - 1) / HZ_W, x0, x1, y0, y1, lane))
+            continue;
         const CapsuleScreen cs = capsule_screen(f, A, B, radius);
         const float pad = cs.pad - 11.4f + 1.0f;                       // pixel half diagonal instead of the tile's
         const float ex = cs.bi - cs.ai, ey = cs.bj - cs.aj, ee = ex * ex + ey * ey;
@@ -322,73 +327,210 @@ __device__ __forceinline__ bool triangle_depth(const float* v0, const float* v1,
 // one to a few pixels for a 2.5 mm triangle — and runs the VA-3 test on those pixel centres only, merging hits
 // with atomicMin.  Same (pixel, triangle) arithmetic as testing every pixel against every triangle; the min is
 // order independent.  A triangle with a vertex at or behind the eye plane takes the instance's whole screen box.
+//
+// Occlusion cull (dense scenes: 100 k droplets of ~300 pixels each bury one another a hundred deep — 6 % of C4D's
+// droplets show a pixel): the frame's droplets are sorted into DROP_SLABS depth slabs (k_droplet_depth_bins /
+// k_droplet_slab_edges / k_droplet_slab_order) and rasterised nearest slab first; after every slab k_hiz_from_vis turns the keys so far into the
+// farthest depth per 8x4 pixel block, and the next slab drops every instance whose bounding sphere lies entirely behind
+// the farthest winner of every block its screen box touches: it cannot win a pixel, so the keys are the same with the
+// cull on or off.  (A subsample as occluders, like the sphere path's pre-pass, culled 28 % here: a droplet's box spans
+// thirty blocks and a sparse sample leaves holes in them; the slabs in front of a droplet hold everything that hides it.)
+// order == NULL: one pass over everything, no cull.
+constexpr int DROP_SLABS = 8, DROP_BINS = 256;
+// cumulative share of a frame's droplets in front of slab s (sixty-fourths): thin slabs in front, where the visible
+// surface is; the deep half of the cloud goes in two passes that the Hi-Z empties almost completely
+__constant__ int c_slab_share[DROP_SLABS + 1] = {0, 1, 2, 4, 8, 16, 32, 48, 64};
+
 __global__ void __launch_bounds__(256)
 k_raster_droplets(const FrameDev* __restrict__ frames, long long n, DropletMeshDev mesh, uint32_t id_base, const float* __restrict__ xf,
-                  unsigned long long* __restrict__ vis, long long vis_stride)
+                  unsigned long long* __restrict__ vis, long long vis_stride, const int* __restrict__ order, const int* __restrict__ starts,
+                  int slab, const unsigned int* __restrict__ hz, int hz_stride, unsigned long long* __restrict__ dbg)
 {
+    // persistent: the grid's warps stride over the slab's droplet list (order == NULL: droplets 0..n-1)
     extern __shared__ __align__(16) float s_cam[];   // [warps][nv][3] camera-space vertices
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-    const long long i = (long long)blockIdx.x * warps + warp;
-    if (i >= n) return;
     const FrameDev& f = frames[b];
-    const float* M = xf + ((size_t)b * n + i) * 12;
-    float m[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) m[k] = __ldg(M + k);
-    // instance bounding sphere -> screen box (also the early out for droplets off screen / behind the eye)
-    int bx0 = 0, bx1 = -1, by0 = 0, by1 = -1;
-    {
-        const float4 o = mesh.bound;
-        const float X[3] = {m[2] * o.z + m[3], m[6] * o.z + m[7], m[10] * o.z + m[11]};
-        float c[3];
-        to_camera(f, X, c);
-        const float R = o.w * 1.01f + 1e-5f + 4e-6f * (fabsf(c[0]) + fabsf(c[1]) + fabsf(c[2]));
-        if (!(isfinite(m[0] + m[1] + m[2] + m[4] + m[5] + m[6] + m[8] + m[9] + m[10]) && sphere_bbox(f, c[0], c[1], c[2], R, bx0, bx1, by0, by1)))
-            return;                                  // warp-uniform
-    }
+    const int first = order ? __ldg(starts + b * (DROP_SLABS + 1) + slab) : 0;
+    const long long count = order ? (long long)(__ldg(starts + b * (DROP_SLABS + 1) + slab + 1) - first) : n;
+    const int* list = order ? order + (size_t)b * n + first : nullptr;
     float* cam = s_cam + (size_t)warp * mesh.nv * 3;
-    for (int v = lane; v < mesh.nv; v += 32) {
-        const float ox = __ldg(mesh.verts + 3 * v), oy = __ldg(mesh.verts + 3 * v + 1), oz = __ldg(mesh.verts + 3 * v + 2);
-        float X[3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) X[r] = fmaf(m[4 * r], ox, fmaf(m[4 * r + 1], oy, fmaf(m[4 * r + 2], oz, m[4 * r + 3])));
-        to_camera(f, X, cam + 3 * v);
-    }
-    __syncwarp();
     unsigned long long* out = vis + (size_t)b * vis_stride;
-    const unsigned long long id = (unsigned long long)(id_base + (uint32_t)i);
     const int ns = mesh.n_segs, ntri = 2 * mesh.n_rings * ns;
-    for (int t = lane; t < ntri; t += 32) {
-        const int quad = t >> 1, r = quad / ns, j = quad - r * ns, jn = j + 1 == ns ? 0 : j + 1;
-        const float* ring0 = cam + 3 * r * ns;
-        const float* ring1 = ring0 + 3 * ns;
-        // the reference's faces per quad: (v0, v2, v1) and (v1, v2, v3)
-        const float* v0 = (t & 1) ? ring0 + 3 * jn : ring0 + 3 * j;
-        const float* v1 = ring1 + 3 * j;
-        const float* v2 = (t & 1) ? ring1 + 3 * jn : ring0 + 3 * jn;
-        int x0 = bx0, x1 = bx1, y0 = by0, y1 = by1;
-        if (v0[2] > 1e-3f && v1[2] > 1e-3f && v2[2] > 1e-3f) {
-            float i0, j0, i1, j1, i2, j2;
-            pixel_of(f, v0[0], v0[1], v0[2], i0, j0);
-            pixel_of(f, v1[0], v1[1], v1[2], i1, j1);
-            pixel_of(f, v2[0], v2[1], v2[2], i2, j2);
-            // A pixel centre can pass VA-3 only inside the projected triangle, up to the float error of the
-            // barycentrics — which, in pixels, grows as the triangle turns edge-on (error ~1e-4 of an edge length
-            // divided by the cosine of the tilt).  Half a pixel of padding covers tilts down to cos ~ 2e-4.
-            constexpr float PAD = 0.5f;
-            x0 = max(x0, (int)ceilf(fminf(i0, fminf(i1, i2)) - PAD)); x1 = min(x1, (int)floorf(fmaxf(i0, fmaxf(i1, i2)) + PAD));
-            y0 = max(y0, (int)ceilf(fminf(j0, fminf(j1, j2)) - PAD)); y1 = min(y1, (int)floorf(fmaxf(j0, fmaxf(j1, j2)) + PAD));
+    for (long long k = (long long)blockIdx.x * warps + warp; k < count; k += (long long)gridDim.x * warps) {
+        const long long i = list ? (long long)__ldg(list + k) : k;
+        const float* M = xf + ((size_t)b * n + i) * 12;
+        float m[12];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) m[q] = __ldg(M + q);
+        // instance bounding sphere -> screen box (also the early out for droplets off screen / behind the eye)
+        int bx0 = 0, bx1 = -1, by0 = 0, by1 = -1;
+        {
+            const float4 o = mesh.bound;
+            const float X[3] = {m[2] * o.z + m[3], m[6] * o.z + m[7], m[10] * o.z + m[11]};
+            float c[3];
+            to_camera(f, X, c);
+            const float R = o.w * 1.01f + 1e-5f + 4e-6f * (fabsf(c[0]) + fabsf(c[1]) + fabsf(c[2]));
+            if (!(isfinite(m[0] + m[1] + m[2] + m[4] + m[5] + m[6] + m[8] + m[9] + m[10]) && sphere_bbox(f, c[0], c[1], c[2], R, bx0, bx1, by0, by1)))
+                continue;                                // warp-uniform
+#ifdef PCR_RASTER_STATS
+            if (lane == 0 && hz) atomicAdd(dbg + 11, 1ull);
+#endif
+            if (hz && nearest_depth_bits(c[2], R) > hiz_far_bits_warp(hz + (size_t)b * hz_stride, (f.W + HZ_W - 1) / HZ_W, bx0, bx1, by0, by1, lane)) {
+#ifdef PCR_RASTER_STATS
+                if (lane == 0) atomicAdd(dbg + 12, 1ull);
+#endif
+                continue;                                // buried (warp-uniform)
+            }
         }
-        for (int py = y0; py <= y1; ++py) {
-            const float w = pix_w(f, py);
-            for (int px = x0; px <= x1; ++px) {
-                float d;
-                if (triangle_depth(v0, v1, v2, pix_u(f, px), w, f.near_clip, f.far_clip, d))
-                    atomicMin(out + (size_t)py * f.W + px, ((unsigned long long)__float_as_uint(d) << 32) | id);
+        __syncwarp();                                    // the previous droplet's triangles are done with the vertices
+        for (int v = lane; v < mesh.nv; v += 32) {
+            const float ox = __ldg(mesh.verts + 3 * v), oy = __ldg(mesh.verts + 3 * v + 1), oz = __ldg(mesh.verts + 3 * v + 2);
+            float X[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) X[r] = fmaf(m[4 * r], ox, fmaf(m[4 * r + 1], oy, fmaf(m[4 * r + 2], oz, m[4 * r + 3])));
+            to_camera(f, X, cam + 3 * v);
+        }
+        __syncwarp();
+        const unsigned long long id = (unsigned long long)(id_base + (uint32_t)i);
+        for (int t = lane; t < ntri; t += 32) {
+            const int quad = t >> 1, r = quad / ns, j = quad - r * ns, jn = j + 1 == ns ? 0 : j + 1;
+            const float* ring0 = cam + 3 * r * ns;
+            const float* ring1 = ring0 + 3 * ns;
+            // the reference's faces per quad: (v0, v2, v1) and (v1, v2, v3)
+            const float* v0 = (t & 1) ? ring0 + 3 * jn : ring0 + 3 * j;
+            const float* v1 = ring1 + 3 * j;
+            const float* v2 = (t & 1) ? ring1 + 3 * jn : ring0 + 3 * jn;
+            int x0 = bx0, x1 = bx1, y0 = by0, y1 = by1;
+            if (v0[2] > 1e-3f && v1[2] > 1e-3f && v2[2] > 1e-3f) {
+                float i0, j0, i1, j1, i2, j2;
+                pixel_of(f, v0[0], v0[1], v0[2], i0, j0);
+                pixel_of(f, v1[0], v1[1], v1[2], i1, j1);
+                pixel_of(f, v2[0], v2[1], v2[2], i2, j2);
+                // A pixel centre can pass VA-3 only inside the projected triangle, up to the float error of the
+                // barycentrics — which, in pixels, grows as the triangle turns edge-on (error ~1e-4 of an edge length
+                // divided by the cosine of the tilt).  Half a pixel of padding covers tilts down to cos ~ 2e-4.
+                constexpr float PAD = 0.5f;
+                x0 = max(x0, (int)ceilf(fminf(i0, fminf(i1, i2)) - PAD)); x1 = min(x1, (int)floorf(fmaxf(i0, fmaxf(i1, i2)) + PAD));
+                y0 = max(y0, (int)ceilf(fminf(j0, fminf(j1, j2)) - PAD)); y1 = min(y1, (int)floorf(fmaxf(j0, fmaxf(j1, j2)) + PAD));
+            }
+            for (int py = y0; py <= y1; ++py) {
+                const float w = pix_w(f, py);
+                for (int px = x0; px <= x1; ++px) {
+                    float d;
+                    if (triangle_depth(v0, v1, v2, pix_u(f, px), w, f.near_clip, f.far_clip, d))
+                        atomicMin(out + (size_t)py * f.W + px, ((unsigned long long)__float_as_uint(d) << 32) | id);
+                }
             }
         }
     }
+}
+
+// Depth bin of every droplet of a frame (camera depth of its bounding sphere's centre over [depth of the world origin -+
+// 1.8]: a standardised cloud lies within sqrt(3) of it) and the frame's histogram of them; then the slab edges (bins
+// [edges[s], edges[s+1]) = slab s, nearest first) and the droplet indices in slab order.
+__global__ void __launch_bounds__(256)
+k_droplet_depth_bins(const FrameDev* __restrict__ frames, long long n, float4 bound, const float* __restrict__ xf,
+                     unsigned char* __restrict__ dbin, unsigned int* __restrict__ hist)
+{
+    __shared__ unsigned int s_h[DROP_BINS];
+    const int b = blockIdx.y;
+    const FrameDev& f = frames[b];
+    s_h[threadIdx.x] = 0u;
+    __syncthreads();
+    const float z0 = -(f.D[0] * f.O[0] + f.D[1] * f.O[1] + f.D[2] * f.O[2]) - 1.8f;
+    for (long long i = (long long)blockIdx.x * 1024 + threadIdx.x; i < min(n, (long long)(blockIdx.x + 1) * 1024); i += 256) {
+        const float* M = xf + ((size_t)b * n + i) * 12;
+        const float X[3] = {__ldg(M + 2) * bound.z + __ldg(M + 3), __ldg(M + 6) * bound.z + __ldg(M + 7), __ldg(M + 10) * bound.z + __ldg(M + 11)};
+        const float cz = (X[0] - f.O[0]) * f.D[0] + (X[1] - f.O[1]) * f.D[1] + (X[2] - f.O[2]) * f.D[2];
+        const float t = (cz - z0) * ((float)DROP_BINS / 3.6f);
+        const int bin = t >= 0.0f ? min((int)t, DROP_BINS - 1) : 0;           // NaN -> 0
+        dbin[(size_t)b * n + i] = (unsigned char)bin;
+        atomicAdd(&s_h[bin], 1u);
+    }
+    __syncthreads();
+    if (s_h[threadIdx.x]) atomicAdd(hist + b * DROP_BINS + threadIdx.x, s_h[threadIdx.x]);
+}
+
+__global__ void k_droplet_slab_edges(unsigned int* __restrict__ hist, long long n, int* __restrict__ edges, int* __restrict__ starts, int* __restrict__ cursor)
+{
+    // edges[s] = first depth bin of slab s, starts[s] = droplets in front of it; a slab ends at the first bin boundary at
+    // or beyond its share c_slab_share[s + 1] / 64 of the frame
+    const int b = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    unsigned int* h = hist + b * DROP_BINS;
+    int* e = edges + b * (DROP_SLABS + 1);
+    int* st = starts + b * (DROP_SLABS + 1);
+    long long acc = 0;
+    int s = 1;
+    e[0] = 0; st[0] = 0;
+    for (int k = 0; k < DROP_BINS; ++k) {
+        acc += h[k];
+        h[k] = 0u;                                   // ready for the next batch
+        while (s < DROP_SLABS && acc >= (n * c_slab_share[s] + 63) / 64) { e[s] = k + 1; st[s] = (int)acc; ++s; }
+    }
+    while (s <= DROP_SLABS) { e[s] = DROP_BINS; st[s] = (int)acc; ++s; }
+    for (int k = 0; k < DROP_SLABS; ++k) cursor[b * DROP_SLABS + k] = st[k];
+}
+
+// order[b][starts[s] ...) = the droplets of slab s (any order): per block, shared-memory counts per slab, one range
+// reservation per (block, slab), ranks inside the block
+__global__ void __launch_bounds__(256)
+k_droplet_slab_order(long long n, const unsigned char* __restrict__ dbin, const int* __restrict__ edges, int* __restrict__ cursor,
+                     int* __restrict__ order)
+{
+    __shared__ int s_cnt[DROP_SLABS], s_base[DROP_SLABS], s_edge[DROP_SLABS + 1];
+    const int b = blockIdx.y;
+    if (threadIdx.x < DROP_SLABS) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x <= DROP_SLABS) s_edge[threadIdx.x] = edges[b * (DROP_SLABS + 1) + threadIdx.x];
+    __syncthreads();
+    int slab[4], rank[4];
+    const long long i0 = (long long)blockIdx.x * 1024 + threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const long long i = i0 + q * 256;
+        slab[q] = -1;
+        if (i < n) {
+            const int bin = (int)dbin[(size_t)b * n + i];
+            int s = 0;
+            while (s + 1 < DROP_SLABS && bin >= s_edge[s + 1]) ++s;
+            slab[q] = s;
+            rank[q] = atomicAdd(&s_cnt[s], 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < DROP_SLABS && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(cursor + b * DROP_SLABS + threadIdx.x, s_cnt[threadIdx.x]);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (slab[q] >= 0) order[(size_t)b * n + s_base[slab[q]] + rank[q]] = (int)(i0 + q * 256);
+}
+
+// Level 1 of the Hi-Z straight from a visibility buffer: farthest depth (float bits) per 8x4 pixel block.  One warp per
+// strip of 32 x 4 pixels (four blocks): a lane reads its column's four keys, then a max over each group of 8 lanes.
+__global__ void __launch_bounds__(256)
+k_hiz_from_vis(const FrameDev* __restrict__ frames, const unsigned long long* __restrict__ vis, long long vis_stride,
+               unsigned int* __restrict__ hz, int hz_stride)
+{
+    const int b = blockIdx.z;
+    const FrameDev& f = frames[b];
+    const int W = f.W, H = f.H, hzw = (W + HZ_W - 1) / HZ_W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int px = (blockIdx.x * 8 + warp) * 32 + lane, by = blockIdx.y;          // strip column, block row
+    if ((px & ~31) >= W || by * HZ_H >= H) return;
+    const unsigned long long* v = vis + (size_t)b * vis_stride;
+    unsigned int far_bits = 0u;
+    if (px < W)
+#pragma unroll
+        for (int r = 0; r < HZ_H; ++r) {
+            const int py = by * HZ_H + r;
+            if (py < H) far_bits = max(far_bits, (unsigned int)(v[(size_t)py * W + px] >> 32));
+        }
+    far_bits = max(far_bits, __shfl_xor_sync(0xffffffffu, far_bits, 4));
+    far_bits = max(far_bits, __shfl_xor_sync(0xffffffffu, far_bits, 2));
+    far_bits = max(far_bits, __shfl_xor_sync(0xffffffffu, far_bits, 1));
+    static_assert(HZ_W == 8 && HZ_H == 4, "strip layout");
+    if ((lane & 7) == 0 && px < W) hz[(size_t)b * hz_stride + by * hzw + px / HZ_W] = far_bits;
 }
 
 // radiance leaving a diffuse surface point P with unit normal (nx,ny,nz): emitter + ground bounce

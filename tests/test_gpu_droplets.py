@@ -191,6 +191,37 @@ def test_droplet_scene_matches_oracle(ctx, orc, do, preset, trails, cols, dtype,
         assert saw_trail
 
 
+def test_droplet_occlusion_cull_never_changes_a_key(lib, orc, do):
+    """Dense droplet scene (C4D's shape, shrunk): the occluder pre-pass + Hi-Z cull of pcr_render_droplet_frames only skips
+    buried droplets and trail segments — keys and image identical with the cull forced on (every 4th / 16th droplet as
+    occluders) and off, and equal to the oracle's."""
+    n, W, H, F = 12_000, 640, 360, 2
+    cfg = PRESETS["traj_vel"]
+    traj = moving_trajectory(F, n, 6, seed=77)
+    traj[:, :, :3] *= 0.25                                   # (per-frame standardisation undoes this; kept for a non-unit scale)
+    cams = [cfg.camera(140 + k, 220, W, H) for k in range(F)]
+    style = cfg.style(trails=True)
+    outs = []
+    for mode, step in ((0, 0), (1, 4), (1, 16)):
+        c = _native.Context(device=0, max_points=n, max_w=W, max_h=H, max_batch=2)
+        try:
+            c.set_droplet_mesh(droplets.droplet_vertices(), droplets.N_RINGS, droplets.N_SEGMENTS)
+            c.set_occlusion(mode=mode, step=step)
+            rgba, vis = c.render_droplet_frames(dev(traj), cams, style, want_vis=True)
+            outs.append((keys(vis).copy(), rgba.cpu().numpy()))
+        finally:
+            c.close()
+    for k, im in outs[1:]:
+        np.testing.assert_array_equal(k, outs[0][0])
+        np.testing.assert_array_equal(im, outs[0][1])
+    want, img = oracle_scene(orc, do, cfg, traj, 1, 0, 141, 220, W, H, 1)
+    np.testing.assert_array_equal(outs[2][0][1], want)
+    check_image(outs[2][1][1], img)
+    ids = (want & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    visible = len(np.unique(ids[ids < n]))
+    assert visible < 0.6 * n, f"the scene should bury a good part of its droplets (visible: {visible} of {n})"
+
+
 def test_facade_droplet_renderers(tmp_path, orc, do):
     """TrajectoryRenderer / TrajectoryVelRenderer: process() with history (the reference's per-frame entry) gives
     the same image as the batched whole path, files are named like the reference's, nothing else is written."""
