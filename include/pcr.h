@@ -148,7 +148,7 @@ int pcr_abi_version(void);
 /* Allocates scratch for up to max_points points per frame, max_w x max_h pixels and
  * max_batch frames in flight per launch.  pair_capacity = max (tile, sphere) pairs per
  * frame (0 = default 24*max_points + 65536 up to 262144 points, 12*max_points + 65536 above;
- * 24 bytes of scratch each, 40 once frames with trails are rendered); frames that exceed it take the slower un-binned raster, results are
+ * 24 bytes of scratch each); frames that exceed it take the slower un-binned raster, results are
  * identical.  Synchronous. */
 int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max_h,
                int max_batch, int64_t pair_capacity);
@@ -342,7 +342,9 @@ int pcr_render_droplet_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int
  *                                                               begin_frame before anybody's pushes)
  *   pcr_render_shard_peer                     K2/K3 into the local d_vis + pushes into the owners' rows
  *   barrier  (any collective)                 all pushes have landed
- *   pcr_shade_shard_peer                      K4: pixels this rank won / owns -> image of dst_rank
+ *   pcr_shade_shard_peer                      K4: pixels this rank won / owns -> image of dst_rank (must follow this frame's
+ *                                             pcr_render_shard_peer on the same context with no other render in between: d_vis
+ *                                             holds valid keys only in the tiles that call drew in, and their list lives in the context)
  *   barrier                                   the image on dst_rank is complete; merged rows may be reused
  * Set-up, once: pcr_peer_alloc on every rank, exchange the buffers' IPC handles (pcr_ipc_export / pcr_ipc_open;
  * ranks inside ONE process pass raw pointers), pcr_peer_set.  At most 8 ranks. */

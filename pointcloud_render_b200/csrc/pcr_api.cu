@@ -56,8 +56,7 @@ struct pcr_ctx {
     long long launches = 0;
 
     // scratch, all [max_batch][...]
-    float4* sph = nullptr;            // per survivor: camera-space sphere (cx, cy, cz, r) / capsule end A
-    float4* ext = nullptr;            // per survivor: capsule end B (trails)
+    float4* sph = nullptr;            // per survivor: camera-space sphere (cx, cy, cz, r)
     uint4* rect = nullptr;            // per survivor: pixel bbox + sphere index (K2a -> K2b, K3)
     unsigned int* surv_count = nullptr;
     int gx_cap = 0;
@@ -77,8 +76,7 @@ struct pcr_ctx {
     size_t sample_bytes = 0;
     int sample_prepass = 1;           // PCR_SAMPLE_PREPASS=0 disables (diagnostics)
     int stats_ahead = 1;              // K0 of the next batches on side streams while a batch renders (PCR_STATS_AHEAD=0: in line)
-    float4* p_ext = nullptr;          // capsule end B — allocated when the first frames with trails arrive
-    int raster_ctas_per_sm[2] = {4, 2};   // k_raster_tiles<false / true>: resident CTAs per SM (occupancy query)
+    int raster_ctas_per_sm = 4;       // k_raster_tiles: resident CTAs per SM (occupancy query)
     unsigned long long* stat_pairs = nullptr;
     unsigned int *item_count = nullptr, *item_next = nullptr;
     uint4* items = nullptr;
@@ -133,6 +131,7 @@ struct pcr_ctx {
     void* peer_image = nullptr;
     int peer_w = 0, peer_h = 0;
     PeerDev peer = {};
+    bool peer_tiles_valid = false;    // tile_state holds the tiles the last pcr_render_shard_peer drew in (k_shade_peer)
 
     // droplet scene (pcr_render_droplet_frames): mesh tables, spline plan, per-frame stats of the whole
     // buffer, per-point matrices / control points of one batch — all lazily allocated
@@ -291,7 +290,7 @@ BinDev bin_of(pcr_ctx* c)
 {
     BinDev b;
     b.counts = c->counts; b.offsets = c->offsets; b.cursor = c->cursor;
-    b.p_sph = c->p_sph; b.p_ci = c->p_ci; b.p_ext = c->p_ext; b.tile_state = nullptr;
+    b.p_sph = c->p_sph; b.p_ci = c->p_ci; b.tile_state = nullptr;
     b.scan_part = c->scan_part; b.scan_ready = c->scan_ready; b.scan_stripes = c->scan_stripes;
     b.fill_list = c->fill_list; b.fill_count = c->fill_count;
     b.overflow = c->overflow; b.stat_pairs = c->stat_pairs; b.tiles_cap = c->tiles_cap; b.pair_cap = c->pair_cap;
@@ -546,24 +545,22 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
     const int use_smem = (size_t)tiles * 8 <= (size_t)ctx->smem_optin ? 1 : 0;
     const int resident = ctx->num_sms * (2048 / BIN_THREADS);
     unsigned long long* v = (unsigned long long*)vis;
-    // velocity trails (a second primitive per point) only exist in the fused whole-path entry
+    // velocity trails (a line raster into the finished keys, k_raster_trails) only exist in the fused whole-path entry
     const int trails = raw && st.trails == 1 && raw->cols == 6 ? 1 : 0;
     if (trails && 2 * (unsigned long long)n > 0xFFFFFFF0ull) return fail(ctx, PCR_ERR_INVALID, "too many points for trail ids (n + i)");
     const uint32_t cap_id_base = trails ? (uint32_t)n : 0u;
     // lazy floor fill: tiles in which nothing is drawn get their keys from K4 — only when K4 follows in this very call
     // (trails are merged into the finished keys of every tile with atomicMin: the tiles nothing was binned in need their
     // floor keys first, so frames with trails take the eager fill)
-    const bool lazy = ctx->lazy_fill && rgba != nullptr && push == nullptr && !trails;
+    // The fused peer merge is lazy too: a rank's local keys are only ever read in the tiles its own passes drew in (the
+    // seeded raster, and k_shade_peer through the same tile states), the merged buffer has its own floor keys.
+    const bool lazy = ctx->lazy_fill && (rgba != nullptr || push != nullptr) && !trails;
+    ctx->peer_tiles_valid = lazy && push != nullptr;
     if (lazy) bin.tile_state = ctx->tile_state;
-    if (trails && !ctx->p_ext) {
-        CK(cudaMalloc((void**)&ctx->p_ext, sizeof(float4) * (size_t)ctx->max_batch * (size_t)ctx->pair_cap));
-        bin.p_ext = ctx->p_ext;
-    }
-    if (!trails) bin.p_ext = nullptr;
-    const long long slots = 2 * ctx->max_points;       // survivor slots per frame: sphere + trail per point
+    const long long slots = ctx->max_points;           // survivor slots per frame
 
     // one binning + raster pass over `np` spheres (sphere i = point i*step)
-    auto pass = [&](long long np, int step, const unsigned int* hz, int seeded, int do_trails, const PeerDev& peer, unsigned int* hz_out, int sample_step) -> int {
+    auto pass = [&](long long np, int step, const unsigned int* hz, int seeded, const PeerDev& peer, unsigned int* hz_out, int sample_step) -> int {
         unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((np + 2047) / 2048, std::max(1, 2 * resident / nb)));
         // (films too large for the shared-memory histograms use per-pair global atomics; the same large chunks serve them
         // best — 2048-point chunks made 24 k tiny blocks of a 50 M-point cloud: K2a / K2b 435 / 454 -> 379 / 390 us on C5)
@@ -574,7 +571,7 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
             // warps' rings must fit in shared memory
             const int hz_w1 = (W + HZ_W - 1) / HZ_W, hz_h1 = (H + HZ_H - 1) / HZ_H;
             const size_t sm2 = (size_t)tiles * 4 + (size_t)((hz_w1 + 3) / 4) * ((hz_h1 + 3) / 4) * 4 + (size_t)(BIN_THREADS / 32) * 5 * RING_CAP * 4;
-            const int two_phase = (ctx->two_phase && hz && use_smem && !do_trails && sm2 <= (size_t)ctx->smem_optin / 2) ? 1 : 0;
+            const int two_phase = (ctx->two_phase && hz && use_smem && sm2 <= (size_t)ctx->smem_optin / 2) ? 1 : 0;
             const size_t sm = two_phase ? sm2 : (use_smem ? (size_t)tiles * 4 : 0);
             // the pre-pass reads the compact sample K0 wrote (point i of the pass = sample row i) when there is one
             RawSrc rsrc = raw ? *raw : RawSrc{};
@@ -582,14 +579,12 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
             // (the sample holds every sample_step-th point; a coarser pass strides over it)
             if (raw && step > 1 && raw->sample && step % sample_step == 0) { rsrc.in = raw->sample; rsrc.frame_stride = raw->sample_stride; rsrc.cols = 3; fetch_step = step / sample_step; }
             const RawSrc* rawp = raw ? &rsrc : nullptr;
-#define PCR_PROJECT(T, RAWB, TRB, posarg, strarg, rawarg)                                                                        \
-    LAUNCH(KID_PROJECT, stream, (k_project_count<T, RAWB, TRB><<<grid, BIN_THREADS, sm, stream>>>(                               \
-        posarg, np, strarg, rawarg, st, fetch_step, ctx->d_frames, ctx->sph, ctx->rect, ctx->ext, slots, bin, use_smem, hz, ctx->hz_cap, two_phase, step)))
-            if (!raw) PCR_PROJECT(float, false, false, pos, in_stride, raw_frames<float>(nullptr));
-            else if (raw->is_f64 && do_trails) PCR_PROJECT(double, true, true, nullptr, 0, raw_frames<double>(rawp));
-            else if (raw->is_f64) PCR_PROJECT(double, true, false, nullptr, 0, raw_frames<double>(rawp));
-            else if (do_trails) PCR_PROJECT(float, true, true, nullptr, 0, raw_frames<float>(rawp));
-            else PCR_PROJECT(float, true, false, nullptr, 0, raw_frames<float>(rawp));
+#define PCR_PROJECT(T, RAWB, posarg, strarg, rawarg)                                                                             \
+    LAUNCH(KID_PROJECT, stream, (k_project_count<T, RAWB><<<grid, BIN_THREADS, sm, stream>>>(                                    \
+        posarg, np, strarg, rawarg, st, fetch_step, ctx->d_frames, ctx->sph, ctx->rect, slots, bin, use_smem, hz, ctx->hz_cap, two_phase, step)))
+            if (!raw) PCR_PROJECT(float, false, pos, in_stride, raw_frames<float>(nullptr));
+            else if (raw->is_f64) PCR_PROJECT(double, true, nullptr, 0, raw_frames<double>(rawp));
+            else PCR_PROJECT(float, true, nullptr, 0, raw_frames<float>(rawp));
 #undef PCR_PROJECT
         }
         if (++ctx->scan_epoch == 0u) ctx->scan_epoch = 1u;            // 0 = the flags' initial value
@@ -602,14 +597,8 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         }
         if (np > 0) {
             dim3 grid(gx, nb);
-            BinDev bin_pass = bin;
-            if (!do_trails) bin_pass.p_ext = nullptr;
-            if (do_trails)
-                LAUNCH(KID_SCATTER, stream, k_scatter<true><<<grid, ctx->scatter_threads, use_smem ? tiles * 8 : 0, stream>>>(
-                    np, ctx->d_frames, ctx->sph, ctx->rect, ctx->ext, slots, bin_pass, use_smem, st.trail_radius, id_base, (uint32_t)step, cap_id_base));
-            else
-                LAUNCH(KID_SCATTER, stream, k_scatter<false><<<grid, ctx->scatter_threads, use_smem ? tiles * 8 : 0, stream>>>(
-                    np, ctx->d_frames, ctx->sph, ctx->rect, ctx->ext, slots, bin_pass, use_smem, st.trail_radius, id_base, (uint32_t)step, cap_id_base));
+            LAUNCH(KID_SCATTER, stream, k_scatter<<<grid, ctx->scatter_threads, use_smem ? tiles * 8 : 0, stream>>>(
+                np, ctx->d_frames, ctx->sph, ctx->rect, slots, bin, use_smem, id_base, (uint32_t)step));
         }
         if (!seeded) {
             // floor keys of empty tiles, all-ones preset of split tiles
@@ -618,14 +607,10 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         }
         if (np > 0) {
             // persistent raster: CTAs pull (tile, <= ITEM_SPHERES spheres) items from per-frame queues
-            const int raster_ctas = ctx->num_sms * ctx->raster_ctas_per_sm[do_trails ? 1 : 0];
+            const int raster_ctas = ctx->num_sms * ctx->raster_ctas_per_sm;
             dim3 grid((unsigned)std::max(1, std::min(raster_ctas, tiles * nb)));
-            if (do_trails)
-                LAUNCH(KID_RASTER, stream, k_raster_tiles<true><<<grid, RASTER_CTA_THREADS, sizeof(RasterStage<true>) * RASTER_STAGES, stream>>>(
-                    ctx->d_frames, st, ctx->sph, ctx->rect, ctx->ext, slots, bin, id_base, (uint32_t)step, cap_id_base, v, vis_stride, nb, np, seeded, (int)gx, peer, hz_out, ctx->hz_cap));
-            else
-                LAUNCH(KID_RASTER, stream, k_raster_tiles<false><<<grid, RASTER_CTA_THREADS, sizeof(RasterStage<false>) * RASTER_STAGES, stream>>>(
-                    ctx->d_frames, st, ctx->sph, ctx->rect, ctx->ext, slots, bin, id_base, (uint32_t)step, 0u, v, vis_stride, nb, np, seeded, (int)gx, peer, hz_out, ctx->hz_cap));
+            LAUNCH(KID_RASTER, stream, k_raster_tiles<<<grid, RASTER_CTA_THREADS, sizeof(RasterStage) * RASTER_STAGES, stream>>>(
+                ctx->d_frames, st, ctx->sph, ctx->rect, slots, bin, id_base, (uint32_t)step, v, vis_stride, nb, np, seeded, (int)gx, peer, hz_out, ctx->hz_cap));
         }
         return PCR_OK;
     };
@@ -647,27 +632,27 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         // -> Hi-Z B (which starts as a copy of A: tiles the second pass does not touch keep their entries); then all points
         const int s1 = ctx->occlusion_step2, s0 = s1 * ctx->occlusion_ratio;
         if (!ctx->hz_b) CK(cudaMalloc((void**)&ctx->hz_b, sizeof(unsigned int) * (size_t)ctx->max_batch * (size_t)ctx->hz_cap));
-        int rc = pass((n + s0 - 1) / s0, s0, nullptr, 0, 0, no_peer, ctx->hz, s1);
+        int rc = pass((n + s0 - 1) / s0, s0, nullptr, 0, no_peer, ctx->hz, s1);
         if (rc) return rc;
         if ((rc = finish_hiz(ctx->hz, lazy ? 1 : 0))) return rc;
         CK(cudaMemcpyAsync(ctx->hz_b, ctx->hz, sizeof(unsigned int) * (size_t)nb * (size_t)ctx->hz_cap, cudaMemcpyDeviceToDevice, stream));
-        rc = pass((n + s1 - 1) / s1, s1, ctx->hz, 1, 0, no_peer, ctx->hz_b, s1);
+        rc = pass((n + s1 - 1) / s1, s1, ctx->hz, 1, no_peer, ctx->hz_b, s1);
         if (rc) return rc;
         if ((rc = finish_hiz(ctx->hz_b, 0))) return rc;             // (the seeded scan's list holds other tiles: look at every tile)
-        rc = pass(n, 1, ctx->hz_b, 1, 0, peer_final, nullptr, s1);
+        rc = pass(n, 1, ctx->hz_b, 1, peer_final, nullptr, s1);
         trail_hz = ctx->hz_b;
         if (rc) return rc;
     } else if (occl && n > ctx->occlusion_step) {
         // occluder pre-pass (every step-th point, true ids) -> Hi-Z -> main pass seeded with its keys
         const int step = ctx->occlusion_step;
-        int rc = pass((n + step - 1) / step, step, nullptr, 0, 0, no_peer, ctx->hz, step);       // trails are never occluders; only the final pass pushes
+        int rc = pass((n + step - 1) / step, step, nullptr, 0, no_peer, ctx->hz, step);       // only the final pass pushes to the peers
         if (rc) return rc;
         if ((rc = finish_hiz(ctx->hz, lazy ? 1 : 0))) return rc;
-        rc = pass(n, 1, ctx->hz, 1, 0, peer_final, nullptr, step);
+        rc = pass(n, 1, ctx->hz, 1, peer_final, nullptr, step);
         trail_hz = ctx->hz;
         if (rc) return rc;
     } else {
-        int rc = pass(n, 1, nullptr, 0, 0, peer_final, nullptr, 1);
+        int rc = pass(n, 1, nullptr, 0, peer_final, nullptr, 1);
         if (rc) return rc;
     }
     if (trails) {
@@ -736,8 +721,8 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     pcr_ctx* ctx = new (std::nothrow) pcr_ctx();
     if (!ctx) return PCR_ERR_NOMEM;
     ctx->device = device; ctx->max_points = max_points; ctx->max_w = max_w; ctx->max_h = max_h; ctx->max_batch = max_batch;
-    // a pair costs 24 bytes (40 with trails): the default leaves room for 24 tile entries per point up to 262144
-    // points (trails cross many tiles), 12 above (+ padding of every tile's range to a multiple of 4); a frame that
+    // a pair costs 24 bytes: the default leaves room for 24 tile entries per point up to 262144 points (large
+    // projected spheres on small clouds), 12 above (+ padding of every tile's range to a multiple of 4); a frame that
     // needs more takes the unbinned raster (overflow path)
     ctx->pair_cap = pair_capacity > 0 ? pair_capacity : (max_points <= 262144 ? 24 : 12) * max_points + 65536;
     if (ctx->pair_cap > 0xFFFFFFF0ll) ctx->pair_cap = 0xFFFFFFF0ll;
@@ -766,11 +751,9 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     if (e == cudaSuccess) {
         ctx->num_sms = prop.multiProcessorCount;
         ctx->smem_optin = (int)std::min<size_t>(prop.sharedMemPerBlockOptin, 200 * 1024);
-        e = cudaFuncSetAttribute(k_project_count<float, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<float, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<float, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<double, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<double, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+        e = cudaFuncSetAttribute(k_project_count<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         {
             const int mean_smem = (int)(MEAN_SMEM_PER_FRAME * MEAN_FRAMES_PER_BLOCK);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mean_sequential<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mean_smem);
@@ -778,18 +761,14 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mean_sequential<double, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mean_smem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mean_sequential<double, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, mean_smem);
         }
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_raster_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(RasterStage<false>) * RASTER_STAGES));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_raster_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(RasterStage<true>) * RASTER_STAGES));
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->raster_ctas_per_sm[0], k_raster_tiles<false>, RASTER_CTA_THREADS, sizeof(RasterStage<false>) * RASTER_STAGES);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->raster_ctas_per_sm[1], k_raster_tiles<true>, RASTER_CTA_THREADS, sizeof(RasterStage<true>) * RASTER_STAGES);
-        if (e == cudaSuccess && (ctx->raster_ctas_per_sm[0] < 1 || ctx->raster_ctas_per_sm[1] < 1)) e = cudaErrorLaunchOutOfResources;
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_raster_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(RasterStage) * RASTER_STAGES));
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->raster_ctas_per_sm, k_raster_tiles, RASTER_CTA_THREADS, sizeof(RasterStage) * RASTER_STAGES);
+        if (e == cudaSuccess && ctx->raster_ctas_per_sm < 1) e = cudaErrorLaunchOutOfResources;
     }
 #define ALLOC(ptr, bytes) if (e == cudaSuccess) e = cudaMalloc((void**)&(ptr), (bytes))
-    ALLOC(ctx->sph, sizeof(float4) * B * N * 2);       // 2 survivor slots per point: its sphere and its trail
-    ALLOC(ctx->ext, sizeof(float4) * B * N * 2);
-    ALLOC(ctx->rect, sizeof(uint4) * B * N * 2);
+    ALLOC(ctx->sph, sizeof(float4) * B * N);
+    ALLOC(ctx->rect, sizeof(uint4) * B * N);
     ctx->gx_cap = (int)std::max<long long>(2 * ctx->num_sms * (2048 / BIN_THREADS), (max_points + BIN_THREADS * 4 - 1) / (BIN_THREADS * 4)) + 1;
     ALLOC(ctx->surv_count, sizeof(unsigned int) * B * (size_t)ctx->gx_cap);
     ALLOC(ctx->partials, sizeof(double) * B * MAX_STAT_BLOCKS * 9 * (PREP_SLOTS + 1));   // one region per prepared-batch slot + the in-line one
@@ -837,8 +816,8 @@ void pcr_destroy(pcr_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    void* frees[] = {ctx->surv_count, ctx->ext, ctx->sph, ctx->rect, ctx->partials, ctx->stats, ctx->done, ctx->counts, ctx->offsets,
-                     ctx->cursor, ctx->p_sph, ctx->p_ci, ctx->p_ext, ctx->tile_state, ctx->sample, ctx->scan_part, ctx->scan_ready, ctx->fill_list, ctx->fill_count, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->hz_b, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_radius, ctx->stage_rgb,
+    void* frees[] = {ctx->surv_count, ctx->sph, ctx->rect, ctx->partials, ctx->stats, ctx->done, ctx->counts, ctx->offsets,
+                     ctx->cursor, ctx->p_sph, ctx->p_ci, ctx->tile_state, ctx->sample, ctx->scan_part, ctx->scan_ready, ctx->fill_list, ctx->fill_count, ctx->overflow, ctx->stat_pairs, ctx->item_count, ctx->item_next, ctx->items, ctx->hz, ctx->hz_b, ctx->lut, ctx->vis, ctx->d_frames, ctx->stage_radius, ctx->stage_rgb,
                      ctx->peer_merged, ctx->peer_image, ctx->mesh_verts, ctx->mesh_prof, ctx->plan, ctx->dstats, ctx->dxf, ctx->dctrl, ctx->dcount, ctx->dbin, ctx->dhist, ctx->dedges, ctx->dstarts, ctx->dcursor, ctx->dorder};
     for (void* p : frees) if (p) cudaFree(p);
     if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
@@ -1798,11 +1777,17 @@ int pcr_shade_shard_peer(pcr_ctx* ctx, const uint64_t* d_vis, const void* d_in, 
     FloorLut lut;
     if ((rc = floor_lut(ctx, st, s, &lut))) return rc;
     const RawSrc raw = {d_in, in_is_f64, n * cols, cols, d_stats10, d_radius, d_rgb};
-    dim3 grid((unsigned)((cam->width + 63) / 64), (unsigned)((cam->height + 3) / 4));
+    // one block per tile this rank has something to do in (drawn in, or inside its row band); the rest are skipped
+    const int tiles = ((cam->width + TILE - 1) / TILE) * ((cam->height + TILE - 1) / TILE);
+    const unsigned grid = (unsigned)std::max(1, std::min(tiles, ctx->num_sms * 16));
+    // (with the lazy floor fill the local keys only exist in the tiles the render call drew in: its tile states must still be there)
+    if (ctx->lazy_fill && !ctx->peer_tiles_valid)
+        return fail(ctx, PCR_ERR_INVALID, "pcr_shade_shard_peer must follow the pcr_render_shard_peer of the same frame on this context (no other render in between)");
+    const unsigned int* tstate = ctx->peer_tiles_valid ? ctx->tile_state : nullptr;
     if (in_is_f64)
-        LAUNCH(KID_SHADE_PEER, s, k_shade_peer<double><<<grid, 256, 0, s>>>(ctx->d_frames, st, lut, d_vis, raw_frames<double>(&raw), n, id_base, ctx->peer));
+        LAUNCH(KID_SHADE_PEER, s, k_shade_peer<double><<<grid, 256, 0, s>>>(ctx->d_frames, st, lut, d_vis, raw_frames<double>(&raw), n, id_base, ctx->peer, tstate));
     else
-        LAUNCH(KID_SHADE_PEER, s, k_shade_peer<float><<<grid, 256, 0, s>>>(ctx->d_frames, st, lut, d_vis, raw_frames<float>(&raw), n, id_base, ctx->peer));
+        LAUNCH(KID_SHADE_PEER, s, k_shade_peer<float><<<grid, 256, 0, s>>>(ctx->d_frames, st, lut, d_vis, raw_frames<float>(&raw), n, id_base, ctx->peer, tstate));
     return leave(ctx, s);
 }
 
