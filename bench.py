@@ -761,15 +761,39 @@ def main():
         cp1.record()
         torch.cuda.synchronize()
         h2d_gbs = 3 * B * spec["input_bytes_per_frame"] / (cp0.elapsed_time(cp1) * 1e-3) / 1e9
-        del dst
-        h2d_all = [h2d_gbs]
+        # the host fabric under the traffic pattern of the pipeline: every rank copies a step's input H2D and a step's images
+        # D2H at the same time, all ranks together (what the box's PCIe switches / host memory give to N GPUs at once)
+        img_dev = torch.empty((B, H, W, 4), dtype=torch.uint8, device="cuda")
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        s_in.wait_event(b0)
+        s_out.wait_event(b0)
+        for _ in range(3):
+            with torch.cuda.stream(s_in):
+                dst.copy_(host[:B], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                host_rgba[0].copy_(img_dev, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(s_in)
+        torch.cuda.current_stream().wait_stream(s_out)
+        b1.record()
+        torch.cuda.synchronize()
+        bidir_s = b0.elapsed_time(b1) * 1e-3
+        bidir = [3 * B * spec["input_bytes_per_frame"] / bidir_s / 1e9, 3 * B * W * H * 4 / bidir_s / 1e9]
+        h2d_all, bidir_all = [h2d_gbs], [bidir]
         if world > 1:
-            t = torch.tensor([h2d_gbs], dtype=torch.float64, device="cuda")
+            t = torch.tensor([h2d_gbs] + bidir, dtype=torch.float64, device="cuda")
             g = [torch.empty_like(t) for _ in range(world)]
             dist.all_gather(g, t)
-            h2d_all = [float(x.item()) for x in g]
+            h2d_all = [float(x[0].item()) for x in g]
+            bidir_all = [[float(x[1].item()), float(x[2].item())] for x in g]
         e2e = {"value": frames_total / e2e_s, "unit": "frames/s", "pcie_h2d_gbs_measured": h2d_gbs, "pcie_h2d_gbs_per_rank": h2d_all,
                "h2d_copy_bound_frames_per_s": sum(h2d_all) * 1e9 / spec["input_bytes_per_frame"],
+               "host_fabric_probe": {"what": "all ranks at once: a step's input H2D and a step's images D2H concurrently, pinned memory, 3 repeats",
+                                     "h2d_gbs_per_rank": [x[0] for x in bidir_all], "d2h_gbs_per_rank": [x[1] for x in bidir_all],
+                                     "h2d_gbs_sum": sum(x[0] for x in bidir_all), "d2h_gbs_sum": sum(x[1] for x in bidir_all),
+                                     "frames_per_s_bound": sum(x[0] for x in bidir_all) * 1e9 / spec["input_bytes_per_frame"]},
                "h2d_bytes_per_step": int(B * spec["input_bytes_per_frame"] + (n * 4 if spec["radii"] else 0)),
                "d2h_bytes_per_step": int(B * W * H * 4), "ms_per_step": e2e_s / args.steps * 1e3,
                "api": "pcr_render_frames_host_submit / pcr_host_wait (pinned host trajectory in, pinned host RGBA8 out; copies overlap "
