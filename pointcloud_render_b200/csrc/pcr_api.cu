@@ -90,6 +90,7 @@ struct pcr_ctx {
     int occlusion = -1;               // -1 auto (n >= occlusion_min_points), 0 off, 1 always
     int scatter_threads = BIN_THREADS; // K2b threads per chunk (PCR_SCATTER_THREADS: diagnostics)
     int two_phase = 1;                // K2a's coarse-then-fine Hi-Z cull (PCR_TWO_PHASE=0 disables: diagnostics)
+    int cull4 = 1;                    // k_project_cull4 where it applies (PCR_CULL4=0 disables: diagnostics)
     int occlusion_step = 16;          // the pre-pass rasterises every step-th point
     long long occlusion_min_points = 1 << 17;
     // Two nested pre-passes for large clouds (n >= occlusion_min_points2): every (step2 * ratio)-th point first, then every
@@ -363,10 +364,10 @@ int launch_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, long long n, int
     // the reference's own (sequential, input-dtype) mean replaces the f64 one unless the caller asked for PCR_MEAN_F64
     const bool sequential = finalize == 1 && mean_mode != PCR_MEAN_F64;
     if (sequential) {
-        // one warp per frame, MEAN_FRAMES_PER_BLOCK frames per block; the dynamic shared memory request keeps a block alone on its SM
-        const int mean_blocks = (nb + MEAN_FRAMES_PER_BLOCK - 1) / MEAN_FRAMES_PER_BLOCK;
-        const size_t mean_smem = MEAN_SMEM_PER_FRAME * MEAN_FRAMES_PER_BLOCK;
-#define PCR_MEAN(T, C) LAUNCH(KID_MEAN, stream, (k_mean_sequential<T, C><<<mean_blocks, 32 * MEAN_FRAMES_PER_BLOCK, mean_smem, stream>>>((const T*)d_in, n, frame_stride, stats, nb)))
+        // MEAN_LANES frames per block: three chain warps (one per axis, lane = frame) + one producer warp
+        const int mean_blocks = (nb + MEAN_LANES - 1) / MEAN_LANES;
+        const size_t mean_smem = MEAN_SMEM_BYTES;
+#define PCR_MEAN(T, C) LAUNCH(KID_MEAN, stream, (k_mean_sequential<T, C><<<mean_blocks, 128, mean_smem, stream>>>((const T*)d_in, n, frame_stride, stats, nb)))
         if (in_is_f64) { if (cols == 3) PCR_MEAN(double, 3); else PCR_MEAN(double, 6); }
         else { if (cols == 3) PCR_MEAN(float, 3); else PCR_MEAN(float, 6); }
 #undef PCR_MEAN
@@ -579,12 +580,22 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
             // (the sample holds every sample_step-th point; a coarser pass strides over it)
             if (raw && step > 1 && raw->sample && step % sample_step == 0) { rsrc.in = raw->sample; rsrc.frame_stride = raw->sample_stride; rsrc.cols = 3; fetch_step = step / sample_step; }
             const RawSrc* rawp = raw ? &rsrc : nullptr;
+            // the headline case — float (n,3) frames on 16-byte boundaries, n a multiple of 4, one radius, every point, a Hi-Z to
+            // cull against — takes the four-points-per-thread kernel with the coarse-cell table (k_project_cull4)
+            const size_t sm4 = (size_t)((tiles + 3) & ~3) * 4 + (size_t)((hz_w1 + 3) / 4 + 2) * ((hz_h1 + 3) / 4 + 2) * 16 + (size_t)(BIN_THREADS / 32) * 4 * RING4_CAP * 4;
+            const bool cull4 = ctx->cull4 && raw && !raw->is_f64 && raw->cols == 3 && step == 1 && !raw->radius && hz && use_smem && ctx->two_phase &&
+                               sm4 <= (size_t)ctx->smem_optin / 2 && (np & 3) == 0 && np < (1ll << 31) && ((uintptr_t)raw->in & 15) == 0 &&
+                               ((raw->frame_stride * 4) & 15) == 0;
+            if (cull4) {
+                LAUNCH(KID_PROJECT, stream, (k_project_cull4<<<grid, BIN_THREADS, sm4, stream>>>((const float*)raw->in, np, raw->frame_stride, raw->stats, st, ctx->d_frames,
+                                                                                            ctx->sph, ctx->rect, slots, bin, hz, ctx->hz_cap)));
+            } else
 #define PCR_PROJECT(T, RAWB, posarg, strarg, rawarg)                                                                             \
     LAUNCH(KID_PROJECT, stream, (k_project_count<T, RAWB><<<grid, BIN_THREADS, sm, stream>>>(                                    \
         posarg, np, strarg, rawarg, st, fetch_step, ctx->d_frames, ctx->sph, ctx->rect, slots, bin, use_smem, hz, ctx->hz_cap, two_phase, step)))
-            if (!raw) PCR_PROJECT(float, false, pos, in_stride, raw_frames<float>(nullptr));
+            { if (!raw) PCR_PROJECT(float, false, pos, in_stride, raw_frames<float>(nullptr));
             else if (raw->is_f64) PCR_PROJECT(double, true, nullptr, 0, raw_frames<double>(rawp));
-            else PCR_PROJECT(float, true, nullptr, 0, raw_frames<float>(rawp));
+            else PCR_PROJECT(float, true, nullptr, 0, raw_frames<float>(rawp)); }
 #undef PCR_PROJECT
         }
         if (++ctx->scan_epoch == 0u) ctx->scan_epoch = 1u;            // 0 = the flags' initial value
@@ -735,6 +746,7 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     }
     if (const char* e = getenv("PCR_OCCLUSION")) ctx->occlusion = atoi(e);
     if (const char* e = getenv("PCR_TWO_PHASE")) ctx->two_phase = atoi(e);
+    if (const char* e = getenv("PCR_CULL4")) ctx->cull4 = atoi(e);
     if (const char* e = getenv("PCR_LAZY_FILL")) ctx->lazy_fill = atoi(e);
     if (const char* e = getenv("PCR_SAMPLE_PREPASS")) ctx->sample_prepass = atoi(e);
     if (const char* e = getenv("PCR_STATS_AHEAD")) ctx->stats_ahead = atoi(e);
@@ -755,12 +767,13 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         {
-            const int mean_smem = (int)(MEAN_SMEM_PER_FRAME * MEAN_FRAMES_PER_BLOCK);
+            const int mean_smem = (int)MEAN_SMEM_BYTES;
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mean_sequential<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mean_smem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mean_sequential<float, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, mean_smem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mean_sequential<double, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mean_smem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mean_sequential<double, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, mean_smem);
         }
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_cull4, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_raster_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(RasterStage) * RASTER_STAGES));
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->raster_ctas_per_sm, k_raster_tiles, RASTER_CTA_THREADS, sizeof(RasterStage) * RASTER_STAGES);

@@ -102,6 +102,41 @@ def test_standardize_transform(ctx, orc, dtype, cols, n, preset):
         np.testing.assert_array_equal(attr4[:, 3], orc.compute_color(want)[:, 3])
 
 
+@pytest.mark.parametrize("dtype,cols", [(np.float32, 3), (np.float32, 6), (np.float64, 3), (np.float64, 6)])
+def test_sequential_mean_every_alignment_and_lane(lib, orc, dtype, cols):
+    """k_mean_sequential (three axis warps, lane = frame, bulk copies of the 16-byte aligned interior of every stage): the
+    reference's np.mean bit for bit for frames that start at any offset inside a 16-byte granule, for point counts around
+    the stage and register-set boundaries, and for every lane of a block (frames 0..10 = a full block of 8 + a ragged one).
+    Per frame: stats through pcr_standardize on the frame's slice (one lane); all frames at once: pcr_render_frames keys
+    equal to the keys of the per-frame two-step renders."""
+    cfg = PRESETS["traj_ball"]
+    W, H, F = 96, 64, 11
+    stage_pts = 1536 // (cols * np.dtype(dtype).itemsize)
+    c = _native.Context(device=0, max_points=4096, max_w=W, max_h=H, max_batch=16)
+    try:
+        for n in sorted({1, 2, 3, 5, 15, 16, 17, 31, 33, stage_pts - 1, stage_pts, stage_pts + 1, 2 * stage_pts + 7, 4 * stage_pts,
+                         5 * stage_pts + 31, 1001, 2048, 4095}):
+            rng = np.random.default_rng(n * 7 + cols)
+            traj = np.ascontiguousarray(rng.standard_normal((F, n, cols)) * 0.7 + [3.0, -1.0, 0.25, 0, 0, 0][:cols], dtype=dtype)
+            d = dev(traj)
+            style = cfg.style(mean_mode=_native.MEAN_SEQUENTIAL)
+            for f in range(F):
+                if n > 64 and f not in (0, 1, 2, 3, 7, 8, 10):
+                    continue
+                stats = c.standardize(d[f], style, want_stats=True)[-1].cpu().numpy()
+                want = traj[f][:, :3].mean(axis=0)                      # numpy: sequential sum in the input dtype, one division
+                np.testing.assert_array_equal(stats[:3], want.astype(np.float64), err_msg=f"n={n} frame {f}")
+            if n >= 2:
+                cams = [cfg.camera(3 * f, 40, W, H) for f in range(F)]
+                vis = c.render_frames(d, cams, style, want_vis=True)[1]
+                for f in (0, 5, 7, 8, 10):
+                    pos4, attr4 = c.standardize(d[f], style)
+                    np.testing.assert_array_equal(pos4.cpu().numpy()[:, :3], orc.transform_coordinates(orc.standardize_point_cloud(traj[f]), cfg.flip_x)[:, :3])
+                    assert torch.equal(c.render(pos4, attr4, cams[f], style)[0], vis[f]), f"n={n} frame {f}"
+    finally:
+        c.close()
+
+
 def test_standardize_golden_inputs(ctx, orc, golden):
     """The reference's own outputs (tests/golden/standardize.npz)."""
     g = golden("standardize.npz")
