@@ -651,14 +651,28 @@ def main():
     batches_per_step = -(-B // ctx.max_batch)
     lookahead = 0 if args.no_lookahead else max(1, min(args.lookahead, slots - 1, 5 // batches_per_step))
 
+    hinted = set()
+
+    def hint(s):
+        ka = (s % slots) * B
+        ctx.prefetch_frames(resident[ka:ka + B], style)
+        hinted.add(s)
+
     def step_device(s, cams=None):
         # K0 of step s + lookahead (statistics incl. the serial reference-exact mean, pre-pass sample) is started now
         # on side streams — the hint pcr_prefetch_frames; every step issues exactly one, so K steps = K x K0 + K renders
         k = (s % slots) * B
         if lookahead:
-            ka = ((s + lookahead) % slots) * B
-            ctx.prefetch_frames(resident[ka:ka + B], style)
+            hint(s + lookahead)
+        hinted.discard(s)
         ctx.render_frames(resident[k:k + B], cams if cams is not None else cams_all[k:k + B], style, radius=radius, out_rgba=rgba)
+
+    def prime(first):
+        # steady state at the start of a timed region whatever --warmup is: the hints that the `lookahead` steps BEFORE the
+        # region would have issued (steps first .. first + lookahead - 1), if the warm-up was too short to have issued them
+        for s in range(first, first + lookahead):
+            if s not in hinted:
+                hint(s)
 
     inflight = []
 
@@ -685,6 +699,7 @@ def main():
 
     def timed(n_steps, first, cams_of=None):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        prime(first)
         barrier()
         ev0.record()
         for s in range(n_steps):

@@ -369,11 +369,12 @@ int pcr_shade_shard_peer(pcr_ctx* ctx, const uint64_t* d_vis, const void* d_in, 
 int pcr_counters(pcr_ctx* ctx, int64_t out[4], void* stream);
 
 /* Occlusion pre-pass of pcr_render / pcr_render_frames.  Dense clouds bury most spheres (depth
- * complexity in the hundreds at 1 M points): the pre-pass rasterises every step-th point, builds
- * a per-8x4-pixel farthest-depth map, and the main pass drops every sphere that lies entirely
- * behind it before it is binned.  Purely a work-skipping device: the keys are identical.
+ * complexity in the hundreds at 1 M points): the pre-pass rasterises every step-th point (of the
+ * points behind the cloud's centre plane only every 8th of those: they lose to nearer ones almost
+ * everywhere), builds a per-8x4-pixel farthest-depth map, and the main pass drops every sphere that
+ * lies entirely behind it before it is binned.  Purely a work-skipping device: the keys are identical.
  *   mode -1: automatic (on when n >= min_points; default min_points 131072), 0: off, 1: always
- *   step  0: keep (default 16) ; min_points 0: keep */
+ *   step  0: keep (default 8) ; min_points 0: keep */
 int pcr_set_occlusion(pcr_ctx* ctx, int mode, int step, int64_t min_points);
 
 /* Per-kernel timing.  While enabled, every kernel launch is bracketed by two CUDA events on the

@@ -81,7 +81,8 @@ struct pcr_ctx {
     unsigned int *item_count = nullptr, *item_next = nullptr;
     uint4* items = nullptr;
     int item_cap = 0;
-    int smem_optin = 48 * 1024;       // max dynamic shared memory per block (opt-in)
+    int smem_optin = 48 * 1024;       // max dynamic shared memory per block (opt-in), capped at 200 KB
+    int smem_max = 48 * 1024;         // ... uncapped (the serial mean's exclusive blocks)
     float* lut = nullptr;             // floor form-factor table (LUT_N^2), rebuilt when the scene constants change
     float lut_key[7] = {0, 0, 0, 0, 0, 0, 0};
     bool lut_valid = false;
@@ -90,8 +91,15 @@ struct pcr_ctx {
     int occlusion = -1;               // -1 auto (n >= occlusion_min_points), 0 off, 1 always
     int scatter_threads = BIN_THREADS; // K2b threads per chunk (PCR_SCATTER_THREADS: diagnostics)
     int two_phase = 1;                // K2a's coarse-then-fine Hi-Z cull (PCR_TWO_PHASE=0 disables: diagnostics)
+    // Occluder pre-pass: the sampled spheres deeper than the cloud's centre plane + prepass_zcut (standardised units: the cloud's
+    // largest extent is 1) lose to nearer ones almost everywhere; only every prepass_back-th of them takes part.  Measured on H
+    // (profiles/r02x_*, r02y_*): step 16 / no cut 21.8 k frames/s, step 8 / cut -0.1 / back 8 24.1 k, no back part at all 24.5 k.
+    float prepass_zcut = -0.1f;       // PCR_PREPASS_ZCUT (1e38 = off)
+    int prepass_back = 8;             // ... but every prepass_back-th (a power of two) of those still takes part (PCR_PREPASS_BACK)
+    int scatter_merge = 0;            // K2b blocks take several K2a chunks (PCR_SCATTER_MERGE=1; measured slower on H: 156 vs 124 us per launch)
+    int mean_exclusive = 1;           // the serial mean's blocks keep their SMs to themselves (PCR_MEAN_EXCLUSIVE=0: diagnostics)
     int cull4 = 1;                    // k_project_cull4 where it applies (PCR_CULL4=0 disables: diagnostics)
-    int occlusion_step = 16;          // the pre-pass rasterises every step-th point
+    int occlusion_step = 8;           // the pre-pass rasterises every step-th point (of those in front of prepass_zcut, see below)
     long long occlusion_min_points = 1 << 17;
     // Two nested pre-passes for large clouds (n >= occlusion_min_points2): every (step2 * ratio)-th point first, then every
     // step2-th point culled by the first one's Hi-Z, then all points culled by the second one's — the occluders
@@ -366,7 +374,7 @@ int launch_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, long long n, int
     if (sequential) {
         // MEAN_LANES frames per block: three chain warps (one per axis, lane = frame) + one producer warp
         const int mean_blocks = (nb + MEAN_LANES - 1) / MEAN_LANES;
-        const size_t mean_smem = MEAN_SMEM_BYTES;
+        const size_t mean_smem = ctx->mean_exclusive ? std::max<size_t>(MEAN_SMEM_BYTES, (size_t)ctx->smem_max) : MEAN_SMEM_BYTES;   // see MEAN_SMEM_BYTES
 #define PCR_MEAN(T, C) LAUNCH(KID_MEAN, stream, (k_mean_sequential<T, C><<<mean_blocks, 128, mean_smem, stream>>>((const T*)d_in, n, frame_stride, stats, nb)))
         if (in_is_f64) { if (cols == 3) PCR_MEAN(double, 3); else PCR_MEAN(double, 6); }
         else { if (cols == 3) PCR_MEAN(float, 3); else PCR_MEAN(float, 6); }
@@ -592,7 +600,7 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
             } else
 #define PCR_PROJECT(T, RAWB, posarg, strarg, rawarg)                                                                             \
     LAUNCH(KID_PROJECT, stream, (k_project_count<T, RAWB><<<grid, BIN_THREADS, sm, stream>>>(                                    \
-        posarg, np, strarg, rawarg, st, fetch_step, ctx->d_frames, ctx->sph, ctx->rect, slots, bin, use_smem, hz, ctx->hz_cap, two_phase, step)))
+        posarg, np, strarg, rawarg, st, fetch_step, ctx->d_frames, ctx->sph, ctx->rect, slots, bin, use_smem, hz, ctx->hz_cap, two_phase, step, (hz_out && !hz && step > 1) ? ctx->prepass_zcut : 3.0e38f, (unsigned int)ctx->prepass_back - 1u)))
             { if (!raw) PCR_PROJECT(float, false, pos, in_stride, raw_frames<float>(nullptr));
             else if (raw->is_f64) PCR_PROJECT(double, true, nullptr, 0, raw_frames<double>(rawp));
             else PCR_PROJECT(float, true, nullptr, 0, raw_frames<float>(rawp)); }
@@ -607,9 +615,12 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
             LAUNCH(KID_FILL, stream, k_fill_tiles<<<grid, 256, 0, stream>>>(ctx->d_frames, st, bin, v, vis_stride, nullptr, ctx->hz_cap, 2));
         }
         if (np > 0) {
-            dim3 grid(gx, nb);
+            // a K2b block takes several K2a chunks, so that the whole launch is one wave of resident blocks
+            const int per_frame = std::max(1, PCR_SCATTER_BLOCKS * ctx->num_sms / nb);
+            const int merge = ctx->scatter_merge ? std::min<int>(SCATTER_MERGE_MAX, std::max<int>(1, ((int)gx + per_frame - 1) / per_frame)) : 1;
+            dim3 grid((gx + merge - 1) / merge, nb);
             LAUNCH(KID_SCATTER, stream, k_scatter<<<grid, ctx->scatter_threads, use_smem ? tiles * 8 : 0, stream>>>(
-                np, ctx->d_frames, ctx->sph, ctx->rect, slots, bin, use_smem, id_base, (uint32_t)step));
+                np, ctx->d_frames, ctx->sph, ctx->rect, slots, bin, use_smem, id_base, (uint32_t)step, (int)gx, merge));
         }
         if (!seeded) {
             // floor keys of empty tiles, all-ones preset of split tiles
@@ -628,13 +639,13 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
 
     const bool occl = ctx->occlusion > 0 || (ctx->occlusion < 0 && n >= ctx->occlusion_min_points);
     const unsigned int* trail_hz = nullptr;
-    const int hzn2 = (((W + HZ_W - 1) / HZ_W + 3) / 4) * (((H + HZ_H - 1) / HZ_H + 3) / 4);
+    const int hzn2p = (((W + HZ_W - 1) / HZ_W + 3) / 4 + 2) * (((H + HZ_H - 1) / HZ_H + 3) / 4 + 2);
     // Hi-Z of a finished pre-pass: level-1 entries were written by k_fill_tiles (empty tiles), the scan (untouched tiles, lazy
     // fill) and the raster (single-item tiles); the tiles split into several items are re-read, then level 2 is built
     auto finish_hiz = [&](unsigned int* hzbuf, int listed) -> int {
         dim3 grid((unsigned)(listed ? std::min((tiles + 7) / 8, 8) : (tiles + 7) / 8), nb);
         LAUNCH(KID_HIZ, stream, k_hiz_split<<<grid, 256, 0, stream>>>(ctx->d_frames, bin, v, vis_stride, hzbuf, ctx->hz_cap, listed));
-        dim3 grid2((unsigned)((hzn2 + 255) / 256), nb);
+        dim3 grid2((unsigned)((hzn2p + 255) / 256), nb);                // one thread per cell of the padded level-2 grid
         LAUNCH(KID_HIZ, stream, k_hiz2<<<grid2, 256, 0, stream>>>(ctx->d_frames, hzbuf, ctx->hz_cap));
         return PCR_OK;
     };
@@ -742,11 +753,16 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     ctx->item_cap = ctx->tiles_cap + (int)(ctx->pair_cap / ITEM_SPHERES) + 1;
     {   // level 1 (8x4 pixel blocks) + level 2 (4x4 groups of them), see hiz_far_bits
         const int w1 = (max_w + HZ_W - 1) / HZ_W, h1 = (max_h + HZ_H - 1) / HZ_H;
-        ctx->hz_cap = w1 * h1 + ((w1 + 3) / 4) * ((h1 + 3) / 4);
+        // level 1, level 2, and the coarse-cell table of k_project_cull4 (k_hiz2); a multiple of 4 words: every frame's table is 16-byte aligned
+        ctx->hz_cap = hiz_table_offset(w1, h1) + 4 * ((w1 + 3) / 4 + 2) * ((h1 + 3) / 4 + 2);
     }
     if (const char* e = getenv("PCR_OCCLUSION")) ctx->occlusion = atoi(e);
     if (const char* e = getenv("PCR_TWO_PHASE")) ctx->two_phase = atoi(e);
     if (const char* e = getenv("PCR_CULL4")) ctx->cull4 = atoi(e);
+    if (const char* e = getenv("PCR_MEAN_EXCLUSIVE")) ctx->mean_exclusive = atoi(e);
+    if (const char* e = getenv("PCR_SCATTER_MERGE")) ctx->scatter_merge = atoi(e);
+    if (const char* e = getenv("PCR_PREPASS_ZCUT")) ctx->prepass_zcut = (float)atof(e);
+    if (const char* e = getenv("PCR_PREPASS_BACK")) { int v = std::max(1, atoi(e)); while (v & (v - 1)) v &= v - 1; ctx->prepass_back = v; }
     if (const char* e = getenv("PCR_LAZY_FILL")) ctx->lazy_fill = atoi(e);
     if (const char* e = getenv("PCR_SAMPLE_PREPASS")) ctx->sample_prepass = atoi(e);
     if (const char* e = getenv("PCR_STATS_AHEAD")) ctx->stats_ahead = atoi(e);
@@ -763,11 +779,12 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     if (e == cudaSuccess) {
         ctx->num_sms = prop.multiProcessorCount;
         ctx->smem_optin = (int)std::min<size_t>(prop.sharedMemPerBlockOptin, 200 * 1024);
+        ctx->smem_max = (int)prop.sharedMemPerBlockOptin;
         e = cudaFuncSetAttribute(k_project_count<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project_count<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         {
-            const int mean_smem = (int)MEAN_SMEM_BYTES;
+            const int mean_smem = (int)std::max<size_t>(MEAN_SMEM_BYTES, (size_t)ctx->smem_max);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mean_sequential<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mean_smem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mean_sequential<float, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, mean_smem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mean_sequential<double, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mean_smem);
