@@ -35,8 +35,11 @@ def main():
         k["warp_instructions"] += val(r, "smsp__inst_executed.sum")
         k["us_under_ncu"] += val(r, "gpu__time_duration.sum")
     for name, k in kernels.items():
-        total_inst += k["warp_instructions"]
-        total_dram += k["dram_bytes"]
+        # a step issues exactly ONE K0 (k_stats + the serial mean, for a later step); a capture whose step had no hint yet also
+        # holds that step's own in-line K0: count one launch of each
+        share = 1.0 / k["launches"] if name in ("k_stats", "k_mean_sequential") and k["launches"] > 1 else 1.0
+        total_inst += k["warp_instructions"] * share
+        total_dram += k["dram_bytes"] * share
         k["dram_bytes_per_frame_per_launch"] = k["dram_bytes"] / k["launches"] / frames
         k["warp_instructions_per_frame"] = k["warp_instructions"] / frames
     data = json.load(open(dst)) if os.path.isfile(dst) else {}
