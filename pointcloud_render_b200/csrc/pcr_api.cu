@@ -93,7 +93,7 @@ struct pcr_ctx {
     int two_phase = 1;                // K2a's coarse-then-fine Hi-Z cull (PCR_TWO_PHASE=0 disables: diagnostics)
     // Occluder pre-pass: the sampled spheres deeper than the cloud's centre plane + prepass_zcut (standardised units: the cloud's
     // largest extent is 1) lose to nearer ones almost everywhere; only every prepass_back-th of them takes part.  Measured on H
-    // (profiles/r02x_*, r02y_*): step 16 / no cut 21.8 k frames/s, step 8 / cut -0.1 / back 8 24.1 k, no back part at all 24.5 k.
+    // (profiles/r02xy_prepass_sweep.md): step 16 / no cut 21.8 k frames/s, step 8 / cut -0.1 / back 8 24.1 k, no back part at all 24.5 k.
     float prepass_zcut = -0.1f;       // PCR_PREPASS_ZCUT (1e38 = off)
     int prepass_back = 8;             // ... but every prepass_back-th (a power of two) of those still takes part (PCR_PREPASS_BACK)
     int scatter_merge = 0;            // K2b blocks take several K2a chunks (PCR_SCATTER_MERGE=1; measured slower on H: 156 vs 124 us per launch)
