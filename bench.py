@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with events in the timed region")
+    ap.add_argument("--trace-steps", action="store_true", help="diagnostics: an event after every step of the headline region, per-step ms in the line")
     ap.add_argument("--profile-one-step", action="store_true",
                     help="for ncu --profile-from-start off: warm up, then ONE device-resident step between cudaProfilerStart/Stop, no timing")
     return ap.parse_args()
@@ -697,15 +698,22 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    trace = []
+
     def timed(n_steps, first, cams_of=None):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         prime(first)
         barrier()
         ev0.record()
+        marks = []
         for s in range(n_steps):
             step_device(first + s, cams_of(first + s) if cams_of else None)
+            if args.trace_steps and cams_of is None:
+                marks.append(torch.cuda.Event(enable_timing=True)); marks[-1].record()
         ev1.record()
         barrier()
+        if marks:
+            trace.append([round(a.elapsed_time(b), 3) for a, b in zip([ev0] + marks[:-1], marks)])
         return max_over_ranks(ev0.elapsed_time(ev1))
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -897,6 +905,8 @@ def main():
             "clocks": clocks, "host_placement": numa_all if world > 1 else numa,
             "nvidia_smi_topo": smi_topology()[0][:4000] if world > 1 else None,
             "pairs_last_frame": counters["pairs_last_frame"], "overflow_frames": counters["overflow_frames"]}
+    if trace:
+        line["step_ms"] = trace[0]
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(spec, host_np, radius_np)
     print(json.dumps(line), flush=True)

@@ -96,6 +96,7 @@ struct pcr_ctx {
     // (profiles/r02xy_prepass_sweep.md): step 16 / no cut 21.8 k frames/s, step 8 / cut -0.1 / back 8 24.1 k, no back part at all 24.5 k.
     float prepass_zcut = -0.1f;       // PCR_PREPASS_ZCUT (1e38 = off)
     int prepass_back = 8;             // ... but every prepass_back-th (a power of two) of those still takes part (PCR_PREPASS_BACK)
+    int mean_fused = 1;               // the serial mean's kernel also produces min / max / scale / sample: no k_stats (PCR_MEAN_FUSED=0: diagnostics)
     int scatter_merge = 0;            // K2b blocks take several K2a chunks (PCR_SCATTER_MERGE=1; measured slower on H: 156 vs 124 us per launch)
     int mean_exclusive = 1;           // the serial mean's blocks keep their SMs to themselves (PCR_MEAN_EXCLUSIVE=0: diagnostics)
     int cull4 = 1;                    // k_project_cull4 where it applies (PCR_CULL4=0 disables: diagnostics)
@@ -361,21 +362,29 @@ int launch_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, long long n, int
         blocks = (int)std::min<long long>((n + 2047) / 2048, (2 * ctx->num_sms + nb - 1) / nb);
     blocks = std::min(std::max(blocks, 1), MAX_STAT_BLOCKS);
     dim3 grid(blocks, nb);
+    // the reference's own (sequential, input-dtype) mean replaces the f64 one unless the caller asked for PCR_MEAN_F64; its
+    // kernel then produces the rest of K0 as well (min / max / scale / pre-pass sample: helper warps on the chains' SMs) and
+    // k_stats is not launched at all
+    const bool sequential = finalize == 1 && mean_mode != PCR_MEAN_F64;
+    // (float frames on 16-byte boundaries only: the helpers must keep out of the chains' way, which takes 16-byte loads)
+    const bool aligned16 = !in_is_f64 && ((uintptr_t)d_in % 16 == 0) && (nb == 1 || (frame_stride * 4) % 16 == 0);
+    const bool fused_k0 = sequential && ctx->mean_fused && aligned16;
     // float4 streaming needs 3 columns and every frame base on a 16-byte boundary
-    const int vec = !in_is_f64 && cols == 3 && ((uintptr_t)d_in % 16 == 0) && (nb == 1 || (frame_stride * 4) % 16 == 0);
-    if (in_is_f64)
+    const int vec = aligned16 && cols == 3;
+    if (fused_k0) {
+    } else if (in_is_f64)
         LAUNCH(KID_STATS, stream, k_stats<double><<<grid, 256, 0, stream>>>((const double*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, done, finalize, 0,
                                                                         (double*)sample, sample_stride, (unsigned int)sample_step));
     else
         LAUNCH(KID_STATS, stream, k_stats<float><<<grid, 256, 0, stream>>>((const float*)d_in, n, cols, frame_stride, partials, MAX_STAT_BLOCKS, stats, done, finalize, vec,
                                                                        (float*)sample, sample_stride, (unsigned int)sample_step));
-    // the reference's own (sequential, input-dtype) mean replaces the f64 one unless the caller asked for PCR_MEAN_F64
-    const bool sequential = finalize == 1 && mean_mode != PCR_MEAN_F64;
     if (sequential) {
-        // MEAN_LANES frames per block: three chain warps (one per axis, lane = frame) + one producer warp
+        // MEAN_LANES frames per block: three chain warps (one per axis, lane = frame) + one producer warp (+ the helper warps)
         const int mean_blocks = (nb + MEAN_LANES - 1) / MEAN_LANES;
         const size_t mean_smem = ctx->mean_exclusive ? std::max<size_t>(MEAN_SMEM_BYTES, (size_t)ctx->smem_max) : MEAN_SMEM_BYTES;   // see MEAN_SMEM_BYTES
-#define PCR_MEAN(T, C) LAUNCH(KID_MEAN, stream, (k_mean_sequential<T, C><<<mean_blocks, 128, mean_smem, stream>>>((const T*)d_in, n, frame_stride, stats, nb)))
+        const int mean_threads = fused_k0 ? 128 + 32 * MEAN_HELPERS : 128;
+#define PCR_MEAN(T, C) LAUNCH(KID_MEAN, stream, (k_mean_sequential<T, C><<<mean_blocks, mean_threads, mean_smem, stream>>>((const T*)d_in, n, frame_stride, stats, nb, \
+                                                 fused_k0 ? 1 : 0, fused_k0 ? (T*)sample : nullptr, sample_stride, (unsigned int)std::max(sample_step, 1))))
         if (in_is_f64) { if (cols == 3) PCR_MEAN(double, 3); else PCR_MEAN(double, 6); }
         else { if (cols == 3) PCR_MEAN(float, 3); else PCR_MEAN(float, 6); }
 #undef PCR_MEAN
@@ -761,6 +770,7 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     if (const char* e = getenv("PCR_CULL4")) ctx->cull4 = atoi(e);
     if (const char* e = getenv("PCR_MEAN_EXCLUSIVE")) ctx->mean_exclusive = atoi(e);
     if (const char* e = getenv("PCR_SCATTER_MERGE")) ctx->scatter_merge = atoi(e);
+    if (const char* e = getenv("PCR_MEAN_FUSED")) ctx->mean_fused = atoi(e);
     if (const char* e = getenv("PCR_PREPASS_ZCUT")) ctx->prepass_zcut = (float)atof(e);
     if (const char* e = getenv("PCR_PREPASS_BACK")) { int v = std::max(1, atoi(e)); while (v & (v - 1)) v &= v - 1; ctx->prepass_back = v; }
     if (const char* e = getenv("PCR_LAZY_FILL")) ctx->lazy_fill = atoi(e);
@@ -830,6 +840,18 @@ int pcr_create(pcr_ctx** out, int device, int64_t max_points, int max_w, int max
     if (e == cudaSuccess) e = cudaMemset(ctx->overflow, 0, sizeof(unsigned int) * B);
     if (e == cudaSuccess) e = cudaMemset(ctx->stat_pairs, 0, sizeof(unsigned long long) * (B + 16));
     for (int k = 0; k < RING_SLOTS && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&ctx->ring_ev[k], cudaEventDisableTiming);
+    {
+        // the prepared-batch slots' streams and events, all of them now: created on first use, a slot that had only served
+        // in-line work so far cost its first hint a stream creation — 6 ms of idle GPU in the middle of a pipeline (measured)
+        int lo = 0, hi = 0;
+        if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        for (pcr_ctx::PrepSlot& p : ctx->prep) {
+            if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p.stream, cudaStreamNonBlocking, hi);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.ev_fork, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.ev_ready, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.ev_free, cudaEventDisableTiming);
+        }
+    }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         int code = e == cudaErrorMemoryAllocation ? PCR_ERR_NOMEM : PCR_ERR_CUDA;
@@ -1115,6 +1137,7 @@ int pcr_render_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n, 
         if (rc) return rc;
         int slot = find_prepared(ctx, batch_in(k), in_is_f64, n, cols, nb, style->mean_mode, sp);
         if (slot < 0) {
+            if (getenv("PCR_DEBUG_PREP")) fprintf(stderr, "[pcr] render_frames: batch %p not prepared, K0 in line\n", (const void*)batch_in(k));
             // nobody prepared this batch: on a side stream when more batches follow (their K0 then overlaps this one's
             // render), in line otherwise
             rc = prepare_batch(ctx, batch_in(k), in_is_f64, n, cols, nb, style->mean_mode, sp, s, ahead && nbatches > 1, &slot);
@@ -1159,7 +1182,11 @@ int pcr_prefetch_frames(pcr_ctx* ctx, const void* d_in, int in_is_f64, int64_t n
         if (find_prepared(ctx, in, in_is_f64, n, cols, nb, style->mean_mode, sp) >= 0) continue;
         int free_slots = 0;
         for (const pcr_ctx::PrepSlot& p : ctx->prep) free_slots += !p.valid;
-        if (free_slots <= 1) break;                            // a hint never displaces an earlier one (those frames come first), and one slot stays free for un-hinted work
+        if (free_slots <= 1) {                                 // a hint never displaces an earlier one (those frames come first), and one slot stays free for un-hinted work
+            if (getenv("PCR_DEBUG_PREP")) fprintf(stderr, "[pcr] prefetch_frames: hint %p dropped (no free slot)\n", (const void*)in);
+            break;
+        }
+        if (getenv("PCR_DEBUG_PREP")) fprintf(stderr, "[pcr] prefetch_frames: hint %p prepared\n", (const void*)in);
         int slot;
         if ((rc = prepare_batch(ctx, in, in_is_f64, n, cols, nb, style->mean_mode, sp, s, ctx->stats_ahead != 0, &slot))) return rc;
     }
