@@ -814,6 +814,41 @@ def test_hoisted_scale_division_is_ieee_exact(ctx):
     assert ctx.selftest_scale_div(divisors) == 0
 
 
+@pytest.mark.parametrize("shape", ["cube", "shell", "slab", "two-blobs"])
+def test_prepass_cut_and_cull4_on_other_shapes(lib, orc, shape):
+    """The occluder pre-pass leaves out most of the points behind the cloud's centre plane, and k_project_cull4's first test
+    works on approximate camera-space centres: both are tuned on a Gaussian ball and must stay exact on anything — a uniform
+    cube, a hollow shell (everything visible is near the front, the back is seen through nothing), a thin slab facing the camera
+    (every point within the cut's margin of the centre plane) and two separate blobs (the centre plane lies in the gap between
+    them).  n % 4 == 0 and 3 float columns: the fused entry takes k_project_cull4.  Keys against the oracle fed numpy's
+    standardisation; two cameras of the schedule."""
+    n, W, H = 240_000, 640, 480
+    cfg = PRESETS["traj_ball"].for_trajectory(100)
+    rng = np.random.default_rng(5)
+    if shape == "slab":
+        x = np.column_stack([rng.random(n), 0.02 * rng.random(n), rng.random(n)])        # thin along the axis that becomes depth-ish
+    elif shape == "two-blobs":
+        x = rng.standard_normal((n, 3)) * 0.2 + np.where(rng.random((n, 1)) < 0.5, -1.0, 1.0) * np.array([0.0, 0.0, 1.0])
+    else:
+        x = synthetic.cloud(n, shape, seed=5)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    traj = np.stack([x, x[::-1].copy()])
+    cams = [cfg.camera(10, 100, W, H), cfg.camera(90, 100, W, H)]
+    c = _native.Context(device=0, max_points=n, max_w=W, max_h=H, max_batch=2)
+    try:
+        rgba, vis = c.render_frames(dev(traj), cams, cfg.style(), want_vis=True)
+        assert c.counters()["overflow_frames"] == 0
+        sc = orc_scene(orc, cfg)
+        for f, ci in ((0, 10), (1, 90)):
+            p = orc.transform_coordinates(orc.standardize_point_cloud(traj[f]), cfg.flip_x)
+            pos4 = np.concatenate([p, np.full((n, 1), cfg.radius, np.float32)], axis=1)
+            want = orc.visibility(pos4, orc_frame(orc, cfg, ci, 100, W, H), sc)
+            bad = np.argwhere(keys(vis[f]) != want)
+            assert len(bad) == 0, f"{shape} frame {f}: {len(bad)} pixels differ, first {bad[:3].tolist()}"
+    finally:
+        c.close()
+
+
 @pytest.mark.parametrize("switch", ["PCR_LAZY_FILL", "PCR_SAMPLE_PREPASS", "PCR_TWO_PHASE"])
 def test_work_saving_devices_never_change_a_result(lib, orc, switch, monkeypatch):
     """Lazy floor fill, the compact pre-pass sample written by K0 and the two-phase cull of K2a only move or skip work:
