@@ -374,7 +374,8 @@ int pcr_counters(pcr_ctx* ctx, int64_t out[4], void* stream);
  * everywhere), builds a per-8x4-pixel farthest-depth map, and the main pass drops every sphere that
  * lies entirely behind it before it is binned.  Purely a work-skipping device: the keys are identical.
  *   mode -1: automatic (on when n >= min_points; default min_points 131072), 0: off, 1: always
- *   step  0: keep (default 8) ; min_points 0: keep */
+ *   step  0: keep ; -1: automatic (the default: every 8th point up to 1.5 M points per frame, growing to every 64th
+ *         from 8 M — the pre-pass needs a number of near spheres, not a share of the cloud) ; min_points 0: keep */
 int pcr_set_occlusion(pcr_ctx* ctx, int mode, int step, int64_t min_points);
 
 /* Per-kernel timing.  While enabled, every kernel launch is bracketed by two CUDA events on the

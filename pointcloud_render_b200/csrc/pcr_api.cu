@@ -100,7 +100,8 @@ struct pcr_ctx {
     int scatter_merge = 0;            // K2b blocks take several K2a chunks (PCR_SCATTER_MERGE=1; measured slower on H: 156 vs 124 us per launch)
     int mean_exclusive = 1;           // the serial mean's blocks keep their SMs to themselves (PCR_MEAN_EXCLUSIVE=0: diagnostics)
     int cull4 = 1;                    // k_project_cull4 where it applies (PCR_CULL4=0 disables: diagnostics)
-    int occlusion_step = 8;           // the pre-pass rasterises every step-th point (of those in front of prepass_zcut, see below)
+    int occlusion_step = 0;           // the pre-pass rasterises every step-th point (of those in front of prepass_zcut, see below);
+                                      // 0 = by the size of the cloud (prepass_step): 8 up to 1.5 M points, 64 from 8 M
     long long occlusion_min_points = 1 << 17;
     // Two nested pre-passes for large clouds (n >= occlusion_min_points2): every (step2 * ratio)-th point first, then every
     // step2-th point culled by the first one's Hi-Z, then all points culled by the second one's — the occluders
@@ -392,6 +393,16 @@ int launch_stats(pcr_ctx* ctx, const void* d_in, int in_is_f64, long long n, int
     return PCR_OK;
 }
 
+// Every how-many-th point the occluder pre-pass takes.  What it needs is a roughly constant NUMBER of near spheres — enough to
+// cover the cloud's silhouette a few times over, and a sphere's share of that silhouette does not depend on the film size —
+// so the step grows with the cloud: 8 at the 1 M-point headline (sweep: profiles/r02xy_prepass_sweep.md), 64 for 50 M
+// points (C5 on one GPU, gpurun_out/r03s_*: step 8 543 frames/s, 16 696, 32 790, 64 795).
+int prepass_step(const pcr_ctx* ctx, long long n)
+{
+    if (ctx->occlusion_step > 0) return ctx->occlusion_step;
+    return (int)std::min<long long>(64, std::max<long long>(8, 8 * ((n + 500000) / 1000000)));
+}
+
 double* inline_stats(pcr_ctx* ctx) { return ctx->stats + (size_t)INLINE_REGION * ctx->max_batch * 10; }
 double* slot_stats(pcr_ctx* ctx, int slot) { return ctx->stats + (size_t)slot * ctx->max_batch * 10; }
 
@@ -408,7 +419,7 @@ SamplePlan sample_plan(const pcr_ctx* ctx, long long n)
 {
     const bool occl = ctx->occlusion > 0 || (ctx->occlusion < 0 && n >= ctx->occlusion_min_points);
     SamplePlan sp;
-    sp.sstep = two_prepasses(ctx, n) ? ctx->occlusion_step2 : ctx->occlusion_step;
+    sp.sstep = two_prepasses(ctx, n) ? ctx->occlusion_step2 : prepass_step(ctx, n);
     sp.sampled = ctx->sample_prepass && occl && n > sp.sstep;
     sp.stride = sp.sampled ? ((n + sp.sstep - 1) / sp.sstep) * 3 : 0;
     return sp;
@@ -673,9 +684,9 @@ int launch_render(pcr_ctx* ctx, const float4* pos, const float4* attr, long long
         rc = pass(n, 1, ctx->hz_b, 1, peer_final, nullptr, s1);
         trail_hz = ctx->hz_b;
         if (rc) return rc;
-    } else if (occl && n > ctx->occlusion_step) {
+    } else if (occl && n > prepass_step(ctx, n)) {
         // occluder pre-pass (every step-th point, true ids) -> Hi-Z -> main pass seeded with its keys
-        const int step = ctx->occlusion_step;
+        const int step = prepass_step(ctx, n);
         int rc = pass((n + step - 1) / step, step, nullptr, 0, no_peer, ctx->hz, step);       // only the final pass pushes to the peers
         if (rc) return rc;
         if ((rc = finish_hiz(ctx->hz, lazy ? 1 : 0))) return rc;
@@ -1420,9 +1431,10 @@ int pcr_profile_read(pcr_ctx* ctx, double* ms_out, int64_t* count_out, int capac
 int pcr_set_occlusion(pcr_ctx* ctx, int mode, int step, int64_t min_points)
 {
     if (!ctx) return PCR_ERR_INVALID;
-    if (mode < -1 || mode > 1 || (step != 0 && step < 2)) return fail(ctx, PCR_ERR_INVALID, "pcr_set_occlusion: mode in {-1,0,1}, step >= 2");
+    if (mode < -1 || mode > 1 || (step != 0 && step != -1 && step < 2)) return fail(ctx, PCR_ERR_INVALID, "pcr_set_occlusion: mode in {-1,0,1}, step >= 2 (0 keep, -1 automatic)");
     ctx->occlusion = mode;
-    if (step) { ctx->occlusion_step = step; ctx->occlusion_step2 = std::max(2, step / 2); }
+    if (step == -1) ctx->occlusion_step = 0;                        // by the size of the cloud (prepass_step)
+    else if (step) { ctx->occlusion_step = step; ctx->occlusion_step2 = std::max(2, step / 2); }
     if (min_points > 0) ctx->occlusion_min_points = min_points;
     return PCR_OK;
 }
