@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--workload", default="H", choices=["H", "C2", "C3", "C4", "C5", "C2D", "C4D"])
     ap.add_argument("--points", type=int, default=0, help="override the workload's point count (C5 scaling studies)")
     ap.add_argument("--frames-per-step", type=int, default=0, help="frames per step per GPU (0 = workload default)")
-    ap.add_argument("--max-batch", type=int, default=32, help="frames per internal launch (pcr_create max_batch, <= 64)")
+    ap.add_argument("--max-batch", type=int, default=64, help="frames per internal launch (pcr_create max_batch, <= 64)")
     ap.add_argument("--ring", type=int, default=0, help="resident frames per GPU (0 = enough to exceed L2)")
     ap.add_argument("--trails", action="store_true", help="also draw the reference's velocity trails (6-column workloads C3/C4)")
     ap.add_argument("--merge", default="fused", choices=["fused", "nccl"],
@@ -65,7 +65,7 @@ def parse_args():
 def workload_spec(name, frames_per_step):
     from pointcloud_render_b200 import synthetic
     c = dict(synthetic.CONFIGS[name])
-    default_fps = {"H": 32, "C4": 64, "C3": 64, "C2": 64, "C5": 1, "C2D": 16, "C4D": 8}[name]
+    default_fps = {"H": 64, "C4": 64, "C3": 64, "C2": 64, "C5": 1, "C2D": 16, "C4D": 8}[name]
     c["frames_per_step"] = frames_per_step or default_fps
     b_in = 4 * c["cols"] + (4 if c["radii"] else 0)
     # input read once, u64 visibility written once, RGBA8 written once
