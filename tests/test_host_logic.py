@@ -162,3 +162,28 @@ def test_async_writer_and_naming(tmp_path):
     np.testing.assert_array_equal(np.load(tmp_path / "raw.npy"), frames[0][..., :3])
     with pytest.raises(ValueError):
         output.AsyncImageWriter(fmt="bmp")
+
+
+def test_bench_workloads_and_ring_are_consistent():
+    """bench.py's host-side definitions (no GPU): every workload's ring holds at least five steps (a four-step look-ahead never
+    meets the slice being rendered) of inputs larger than the L2, its slots visit the whole camera schedule, the algorithmic
+    bytes follow SURVEY.md 8d, and the config dict — the same function serves both arms — names what is rendered."""
+    import importlib.util
+    import os
+    spec_ = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(bench)
+    for name in ("H", "C2", "C3", "C4"):
+        spec = bench.workload_spec(name, 0)
+        B = spec["frames_per_step"]
+        assert 1 <= B <= 64
+        ring = bench.ring_frames(spec)
+        assert ring % B == 0 and ring >= 5 * B
+        assert ring * spec["input_bytes_per_frame"] >= 126e6                      # inputs larger than the L2
+        idx = bench.ring_indices(spec, ring)
+        assert len(idx) == ring and set(idx) == set(range(min(spec["frames"], ring))) or len(set(idx)) == min(spec["frames"], ring)
+        b_in = 4 * spec["cols"] + (4 if spec["radii"] else 0)
+        assert spec["algorithmic_bytes_per_frame"] == spec["points"] * b_in + spec["width"] * spec["height"] * 12
+        cfg = bench.config_dict(name, spec, ring, 1)
+        assert cfg["frames_per_step_per_gpu"] == B and cfg["points"] == spec["points"] and name in cfg["workload"]
+    assert bench.workload_spec("H", 0)["points"] == 1_000_000 and bench.workload_spec("H", 16)["frames_per_step"] == 16
